@@ -1,0 +1,70 @@
+"""CPU restatement of the reference's retrieval metrics.  TEST INFRASTRUCTURE.
+
+Follows evaluation/retrieval_metrics.py:14-96 of the reference; pinned by the KATs
+of test/test_evaluation.py:9-22 (recall 1/3, mrr 1/3, ndcg@3 0.23463936301137822).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+ID = Union[int, str]
+
+
+def recall_at_k(retrieved: Sequence[ID], relevant: Sequence[ID], k: int) -> float:
+    """retrieval_metrics.py:14-17."""
+    if not relevant:
+        return 0.0
+    return len(set(retrieved[:k]) & set(relevant)) / len(relevant)
+
+
+def mrr(retrieved: Sequence[ID], relevant: Sequence[ID]) -> float:
+    """retrieval_metrics.py:19-23: reciprocal rank of the first relevant hit."""
+    for rank, d in enumerate(retrieved, 1):
+        if d in relevant:
+            return 1.0 / rank
+    return 0.0
+
+
+def ndcg_at_k(retrieved: Sequence[ID], relevant: Sequence[ID], k: int) -> float:
+    """retrieval_metrics.py:25-31: binary gains, log2(i+2) discount."""
+    dcg = sum(1.0 / math.log2(i + 2) for i, d in enumerate(retrieved[:k]) if d in relevant)
+    idcg = sum(1.0 / math.log2(i + 2) for i in range(min(len(relevant), k)))
+    return dcg / idcg if idcg else 0.0
+
+
+def _parse(metric: str) -> Tuple[str, Optional[int]]:
+    if "@" in metric:
+        name, kk = metric.split("@")
+        return name, int(kk)
+    return metric, None
+
+
+def _one(retrieved, relevant, name: str, k: Optional[int]) -> float:
+    name = name.lower()
+    if name == "recall" and k is not None:
+        return recall_at_k(retrieved, relevant, k)
+    if name == "mrr":
+        return mrr(retrieved[: (k or len(retrieved))], relevant)
+    if name == "ndcg" and k is not None:
+        return ndcg_at_k(retrieved, relevant, k)
+    raise ValueError(f"Metric '{name}' not found.")
+
+
+def evaluate_retrieval(
+    retrieved_batch: List[Sequence[ID]], relevant_batch: List[Sequence[ID]], metrics: List[str]
+) -> Dict[str, Dict[str, float]]:
+    """retrieval_metrics.py:55-96, batch form: per metric the mean and the sample
+    standard deviation (ddof=1; 0.0 for a single query)."""
+    assert len(retrieved_batch) == len(relevant_batch)
+    if not metrics:
+        raise ValueError("No metrics specified.")
+    q = len(retrieved_batch)
+    out: Dict[str, Dict[str, float]] = {}
+    for m in metrics:
+        name, k = _parse(m)
+        vals = [_one(r, rel, name, k) for r, rel in zip(retrieved_batch, relevant_batch)]
+        mean = sum(vals) / q
+        std = math.sqrt(sum((v - mean) ** 2 for v in vals) / (q - 1)) if q > 1 else 0.0
+        out[m] = {"mean": float(mean), "std": float(std)}
+    return out

@@ -1,0 +1,64 @@
+"""Seeded input generators shared by make_golden.py (which stores the reference's
+outputs for them) and by the tests (which feed the same inputs to the oracle and to
+the CUDA path).  numpy's PCG64 stream + float32 casts: deterministic on this image."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+SMALL_CASES = [(100, 10, 64), (1000, 50, 32)]  # test/test_retrieval.py:61
+
+
+def reference_test_embeddings(num: int, dim: int = 64, seed: int = 7) -> torch.Tensor:
+    """The generator of the reference's own retrieval test (test/test_retrieval.py:33-38):
+    default_rng(seed).standard_normal -> fp32 -> rows / (|row| + 1e-12)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((num, dim)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True) + 1e-12
+    return torch.from_numpy(x)
+
+
+def bf16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def edge_case_inputs() -> Tuple[torch.Tensor, torch.Tensor]:
+    """7 x 16 corpus whose row 3 is all zeros; 3 queries whose row 2 is all zeros.
+    Values are multiples of 1/8 in [-2, 2): exact in bf16, so the fp32 reference and
+    the bf16 engine see the same numbers."""
+    rng = np.random.default_rng(11)
+    emb = rng.integers(-16, 16, size=(7, 16)).astype(np.float32) / 8.0
+    emb[3] = 0.0
+    q = rng.integers(-16, 16, size=(3, 16)).astype(np.float32) / 8.0
+    q[2] = 0.0
+    return torch.from_numpy(emb), torch.from_numpy(q)
+
+
+def mid_case_inputs(n: int = 4096, d: int = 384, b: int = 64) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16-representable Gaussian corpus/queries (not normalised: the cosine path
+    normalises, the euclidean path must not); a quarter of the queries are perturbed
+    corpus rows so near neighbours exist."""
+    rng = np.random.default_rng(1234)
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    q = np.random.default_rng(4321).standard_normal((b, d)).astype(np.float32)
+    pick = np.arange(0, b, 4)
+    q[pick] = emb[(pick * 37) % n] + 0.1 * q[pick]
+    return bf16_round(torch.from_numpy(emb)), bf16_round(torch.from_numpy(q))
+
+
+def ae_input(m: int = 48, d: int = 384) -> torch.Tensor:
+    """Unit-norm fp32 rows, like SBERT's normalize_embeddings=True output
+    (retrieval/embedder.py:35-40)."""
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((m, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return torch.from_numpy(x)
+
+
+def metrics_case(q: int = 40, k: int = 10, universe: int = 60) -> Tuple[List[List[int]], List[List[int]]]:
+    rng = np.random.default_rng(5)
+    retrieved = [rng.permutation(universe)[:k].tolist() for _ in range(q)]
+    relevant = [rng.permutation(universe)[: int(rng.integers(1, 4))].tolist() for _ in range(q)]
+    return retrieved, relevant
