@@ -1,0 +1,132 @@
+/*
+ * latentknn.h -- C ABI of liblatentknn.so, the B200 (sm_100a) exact nearest-neighbour
+ * engine behind latent-rag's retriever classes.
+ *
+ * The reference (engares/latent-rag) is pure Python and has no FFI of its own: its
+ * "operator interface" for this path is the duck-typed retriever class contract
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces
+ * (paths relative to the reference tree).  The Python mirror of those classes
+ * (latent_rag_b200/retrieval/) is the only caller; it binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative lk_status on failure; the
+ *     message is available from lk_last_error() (thread local).  Nothing throws.
+ *   - pointers are plain host or device addresses; `mem` says which (lk_mem).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - one thread per handle at a time; handles are not re-entrant.
+ *   - there is no CPU fallback anywhere: without a CUDA device every compute call
+ *     fails with LK_ERR_CUDA.
+ */
+#ifndef LATENTKNN_H
+#define LATENTKNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LK_ABI_VERSION 1
+
+typedef enum lk_status {
+  LK_OK = 0,
+  LK_ERR_INVALID = -1,     /* bad argument                                  */
+  LK_ERR_CUDA = -2,        /* CUDA runtime / launch failure                 */
+  LK_ERR_OOM = -3,         /* device or host allocation failed              */
+  LK_ERR_CAPACITY = -4,    /* lk_index_add past the capacity given at create */
+  LK_ERR_UNSUPPORTED = -5  /* shape outside what the kernels implement      */
+} lk_status;
+
+/* similarity-name options of BruteForceRetriever (retrieval/bruteforce.py:14,49-54);
+ * "mahalanobis" is the README feature (README.md:35) the reference never implemented. */
+typedef enum lk_metric { LK_COSINE = 0, LK_EUCLIDEAN = 1, LK_MAHALANOBIS = 2 } lk_metric;
+typedef enum lk_dtype { LK_F32 = 0, LK_BF16 = 1 } lk_dtype;
+typedef enum lk_mem { LK_HOST = 0, LK_DEVICE = 1 } lk_mem;
+/* which search kernel family to run (LK_KERNEL_AUTO picks by storage / batch / k) */
+typedef enum lk_kernel { LK_KERNEL_AUTO = 0, LK_KERNEL_SIMT = 1, LK_KERNEL_UMMA = 2 } lk_kernel;
+typedef enum lk_ae_kind { LK_AE_DAE = 0, LK_AE_CAE = 1, LK_AE_VAE_MU = 2 } lk_ae_kind;
+
+typedef struct lk_index lk_index;
+typedef struct lk_ae lk_ae;
+
+/* ---- library ----------------------------------------------------------------------- */
+int lk_abi_version(void);
+const char* lk_last_error(void);
+/* number of visible CUDA devices (0 and LK_ERR_CUDA when there is no driver/device) */
+int lk_device_count(int* out_count);
+/* kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t lk_launch_count(void);
+
+/* ---- index: replaces BruteForceRetriever.__init__ (retrieval/bruteforce.py:26-55) and
+ *      FAISSEmbeddingRetriever.build's normalise+add (FAISSEmbeddingRetriever.py:206-257)
+ *
+ * storage LK_BF16: rows are rounded to bf16 and kept as 128-row tcgen05 operand tiles,
+ *                  with one fp32 side value per row (1/|row| for cosine, |row|^2 for the
+ *                  L2 metrics) applied in the kernel epilogue.
+ * storage LK_F32 : rows are kept in fp32 (cosine: pre-normalised like the reference);
+ *                  searched by the exact fp32 FMA kernel.
+ * whiten         : for LK_MAHALANOBIS, the dim x dim row-major fp64 HOST matrix L with
+ *                  precision = L L^T; rows and queries are multiplied by it (fp64
+ *                  accumulate) and then searched with the L2 path.  NULL otherwise.
+ */
+int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, int metric,
+                    int storage, const double* whiten);
+/* append n_rows x dim row-major rows (dtype lk_dtype, host or device) */
+int lk_index_add(lk_index* ix, const void* rows, int dtype, int mem, int64_t n_rows, void* stream);
+int lk_index_size(const lk_index* ix, int64_t* out_rows, int* out_dim);
+/* grow the capacity (device-to-device copy of the tiles); FAISSEmbeddingRetriever.build
+ * appends to an existing index on every call (FAISSEmbeddingRetriever.py:252-257,294-296) */
+int lk_index_reserve(lk_index* ix, int64_t capacity_rows);
+int lk_index_destroy(lk_index* ix);
+
+/* ---- persistence: replaces faiss.write_index / read_index
+ *      (FAISSEmbeddingRetriever.py:65-69,300-304).  The payload is this library's own
+ *      tiled image (not the upstream .faiss format): `tile_bytes` of operand tiles and
+ *      `side_bytes` of fp32 side values covering the rows added so far. */
+int lk_index_storage_bytes(const lk_index* ix, int64_t* out_tile_bytes, int64_t* out_side_bytes);
+int lk_index_export(lk_index* ix, void* tiles_host, void* side_host);
+/* fill an empty index created with the same dim / metric / storage */
+int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host, int64_t n_rows);
+
+/* ---- search: replaces BruteForceRetriever.search (retrieval/bruteforce.py:58-83) and
+ *      FAISSEmbeddingRetriever.search (FAISSEmbeddingRetriever.py:314-326).
+ *
+ * queries     b x dim row-major, q_dtype/q_mem as above
+ * k           1..128; the caller clamps to min(k, rows) like bruteforce.py:81
+ * out_scores  b x k float32, best first, higher = better for every metric
+ * out_idx     b x k int64 row positions + idx_base (idx_base = first global row of a shard)
+ * out_mem     where the two outputs live; for LK_HOST the call returns after the copy
+ * kernel      lk_kernel
+ */
+int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, int64_t b, int k,
+                    float* out_scores, int64_t* out_idx, int out_mem, int64_t idx_base,
+                    int kernel, void* stream);
+/* device time (ms, CUDA events on `stream`) of the search kernel proper and of the whole
+ * device side (query prep + search + merge) of the last lk_index_search on this handle;
+ * used for StatsTracker (retrieval/common.py:37-65) and for bench.py's roofline. */
+int lk_index_last_timing(lk_index* ix, float* out_search_kernel_ms, float* out_total_ms);
+/* enable/disable that event timing (off by default: it synchronises the stream) */
+int lk_index_set_timing(lk_index* ix, int enabled);
+
+/* ---- k-way merge of per-shard candidates (net-new):
+ * cand_* are b x n_lists x list_len, index < 0 or NaN score = padding.  Device or host. */
+int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b,
+                  int n_lists, int list_len, int k, float* out_scores, int64_t* out_idx,
+                  int mem, void* stream);
+
+/* ---- autoencoder encoder forward: replaces DenoisingAutoencoder.encode
+ *      (models/denoising_autoencoder.py:33-34), ContrastiveAutoencoder.encode
+ *      (models/contrastive_autoencoder.py:23-25) and the mu half of
+ *      VariationalAutoencoder.encode (models/variational_autoencoder.py:26-30,
+ *      retrieval/embedder.py:44-45).  Weights are the nn.Linear tensors, fp32 HOST:
+ *      w0 [d_hidden x d_in], b0 [d_hidden], w1 [d_latent x d_hidden], b1 [d_latent]. */
+int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int d_latent,
+                 const float* w0, const float* b0, const float* w1, const float* b1);
+/* x: m x d_in fp32 row-major; z: m x d_latent fp32 row-major */
+int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream);
+int lk_ae_destroy(lk_ae* ae);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LATENTKNN_H */

@@ -1,0 +1,16 @@
+"""latent_rag_b200 -- B200-native exact nearest-neighbour search and autoencoder encoder
+forward behind latent-rag's retriever API.  Hand-written sm_100a CUDA (liblatentknn.so)
+called through a C ABI; Python/PyTorch only for device memory, streams and
+torch.distributed.  No CPU fallback."""
+from . import _native
+from .engine import ExactIndex, merge_topk
+from .retrieval import BruteForceRetriever, FAISSEmbeddingRetriever, StatsTracker, build_retriever
+from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, VariationalAutoencoder,
+                           load_autoencoder)
+from .sharded import ShardedRetriever, shard_bounds
+
+__all__ = [
+    "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
+    "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds",
+]

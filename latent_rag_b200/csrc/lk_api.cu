@@ -1,0 +1,629 @@
+// C ABI of liblatentknn.so (include/latentknn.h): handles, workspaces, staging of host
+// buffers, kernel selection.  No exceptions cross this boundary and nothing here computes
+// on the CPU: without a CUDA device every entry point fails.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "lk_common.cuh"
+
+namespace lk {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  const char* base = strrchr(file, '/');
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line,
+            what);
+  return e == cudaErrorMemoryAllocation ? LK_ERR_OOM : LK_ERR_CUDA;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+// restores the caller's current device (torch tracks it) when an API call returns
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return LK_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)", __FILE__, __LINE__);
+    cap = want;
+    return LK_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+TileGeom make_geom(int dim, int storage) {
+  TileGeom g;
+  g.dim = dim;
+  g.elem_bytes = storage == LK_BF16 ? 2 : 4;
+  g.dim_pad = round_up(dim, storage == LK_BF16 ? kKBlockElems : 4);
+  g.chunks = g.dim_pad * g.elem_bytes / kChunkBytes;
+  return g;
+}
+
+int check_device(int device, int* sm_count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (%d visible)", device, n);
+    return LK_ERR_INVALID;
+  }
+  int major = 0;
+  LK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; liblatentknn is built for sm_100a only", device, major);
+    return LK_ERR_UNSUPPORTED;
+  }
+  LK_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
+  return LK_OK;
+}
+
+constexpr int64_t kStageRows = 1 << 16;  // rows staged per step when the input is on the host
+
+}  // namespace
+}  // namespace lk
+
+using namespace lk;
+
+struct lk_index {
+  int device = 0, sm_count = 0;
+  int dim = 0, metric = 0, kmetric = 0, storage = 0;
+  int side_mode = 0, prenorm = 0;
+  TileGeom g;
+  int64_t capacity = 0, n_rows = 0;
+  unsigned char* tiles = nullptr;
+  float* side = nullptr;
+  double* whiten = nullptr;
+  int* err_flag = nullptr;
+  Buf stage, white, q_tiles, q_side, part_s, part_i, out_s, out_i;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float last_search_ms = 0.f, last_total_ms = 0.f;
+};
+
+struct lk_ae {
+  int device = 0;
+  int kind = 0, d_in = 0, d_hidden = 0, d_latent = 0;
+  float *w0t = nullptr, *b0 = nullptr, *w1t = nullptr, *b1 = nullptr;
+  Buf xin, zout;
+};
+
+extern "C" {
+
+int lk_abi_version(void) { return LK_ABI_VERSION; }
+const char* lk_last_error(void) { return g_err; }
+int64_t lk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int lk_device_count(int* out_count) {
+  if (!out_count) return LK_ERR_INVALID;
+  *out_count = 0;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  *out_count = n;
+  return LK_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// index
+// ------------------------------------------------------------------------------------
+int lk_index_destroy(lk_index* ix) {
+  if (!ix) return LK_OK;
+  DeviceGuard guard(ix->device);
+  if (ix->tiles) cudaFree(ix->tiles);
+  if (ix->side) cudaFree(ix->side);
+  if (ix->whiten) cudaFree(ix->whiten);
+  if (ix->err_flag) cudaFree(ix->err_flag);
+  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->out_s, &ix->out_i};
+  for (Buf* b : bufs) b->release();
+  for (cudaEvent_t e : ix->ev)
+    if (e) cudaEventDestroy(e);
+  delete ix;
+  return LK_OK;
+}
+
+int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, int metric, int storage,
+                    const double* whiten) {
+  if (!out) return LK_ERR_INVALID;
+  *out = nullptr;
+  if (capacity_rows < 1 || capacity_rows > 0x7fffff00LL || dim < 1 || dim > 4096) {
+    set_error("lk_index_create: capacity_rows=%lld dim=%d out of range", (long long)capacity_rows, dim);
+    return LK_ERR_INVALID;
+  }
+  if (metric != LK_COSINE && metric != LK_EUCLIDEAN && metric != LK_MAHALANOBIS) {
+    set_error("Unsupported metric: %d", metric);
+    return LK_ERR_INVALID;
+  }
+  if (storage != LK_F32 && storage != LK_BF16) {
+    set_error("lk_index_create: storage must be LK_F32 or LK_BF16");
+    return LK_ERR_INVALID;
+  }
+  if ((metric == LK_MAHALANOBIS) != (whiten != nullptr)) {
+    set_error("lk_index_create: the whitening matrix is required for mahalanobis and only for it");
+    return LK_ERR_INVALID;
+  }
+  int sm_count = 0;
+  int rc = check_device(device, &sm_count);
+  if (rc != LK_OK) return rc;
+  DeviceGuard guard(device);
+  lk_index* ix = new (std::nothrow) lk_index();
+  if (!ix) return LK_ERR_OOM;
+  ix->device = device;
+  ix->sm_count = sm_count;
+  ix->dim = dim;
+  ix->metric = metric;
+  ix->kmetric = metric == LK_COSINE ? LK_COSINE : LK_EUCLIDEAN;
+  ix->storage = storage;
+  ix->g = make_geom(dim, storage);
+  ix->capacity = capacity_rows;
+  ix->side_mode = ix->kmetric == LK_COSINE ? 0 : 1;
+  ix->prenorm = (ix->kmetric == LK_COSINE && storage == LK_F32) ? 1 : 0;
+  const int64_t nblk = (capacity_rows + kBlockRows - 1) / kBlockRows;
+  const size_t tile_bytes = (size_t)nblk * ix->g.block_bytes();
+  const size_t side_bytes = (size_t)nblk * kBlockRows * sizeof(float);
+#define LK_CREATE_CUDA(expr)                                              \
+  do {                                                                    \
+    cudaError_t _e = (expr);                                              \
+    if (_e != cudaSuccess) {                                              \
+      rc = cuda_fail(_e, #expr, __FILE__, __LINE__);                      \
+      lk_index_destroy(ix);                                               \
+      return rc;                                                          \
+    }                                                                     \
+  } while (0)
+  LK_CREATE_CUDA(cudaMalloc((void**)&ix->tiles, tile_bytes));
+  LK_CREATE_CUDA(cudaMalloc((void**)&ix->side, side_bytes));
+  LK_CREATE_CUDA(cudaMalloc((void**)&ix->err_flag, sizeof(int)));
+  LK_CREATE_CUDA(cudaMemset(ix->tiles, 0, tile_bytes));
+  LK_CREATE_CUDA(cudaMemset(ix->side, 0xFF, side_bytes));  // NaN: rows that do not exist never rank
+  LK_CREATE_CUDA(cudaMemset(ix->err_flag, 0, sizeof(int)));
+  if (whiten) {
+    const size_t wb = (size_t)dim * dim * sizeof(double);
+    LK_CREATE_CUDA(cudaMalloc((void**)&ix->whiten, wb));
+    LK_CREATE_CUDA(cudaMemcpy(ix->whiten, whiten, wb, cudaMemcpyHostToDevice));
+  }
+  for (int i = 0; i < 4; ++i) LK_CREATE_CUDA(cudaEventCreate(&ix->ev[i]));
+#undef LK_CREATE_CUDA
+  *out = ix;
+  return LK_OK;
+}
+
+int lk_index_size(const lk_index* ix, int64_t* out_rows, int* out_dim) {
+  if (!ix) return LK_ERR_INVALID;
+  if (out_rows) *out_rows = ix->n_rows;
+  if (out_dim) *out_dim = ix->dim;
+  return LK_OK;
+}
+
+// rows (host or device, f32/bf16) -> tiles at [row0, row0+n); shared by add and by query prep
+static int ingest_rows(lk_index* ix, const void* rows, int dtype, int mem, int64_t n, void* tiles, float* side,
+                       int64_t row0, cudaStream_t st) {
+  const size_t in_elem = dtype == LK_F32 ? 4 : 2;
+  const bool direct = mem == LK_DEVICE && !ix->whiten;
+  if (direct) return launch_tile_rows(rows, dtype, n, ix->g, tiles, side, row0, ix->side_mode, ix->prenorm, st);
+  for (int64_t done = 0; done < n; done += kStageRows) {
+    const int64_t cnt = n - done < kStageRows ? n - done : kStageRows;
+    const unsigned char* src = static_cast<const unsigned char*>(rows) + (size_t)done * ix->dim * in_elem;
+    const void* cur = src;
+    if (mem == LK_HOST) {
+      int rc = ix->stage.ensure((size_t)kStageRows * ix->dim * in_elem);
+      if (rc != LK_OK) return rc;
+      LK_CUDA(cudaMemcpyAsync(ix->stage.p, src, (size_t)cnt * ix->dim * in_elem, cudaMemcpyHostToDevice, st));
+      cur = ix->stage.p;
+    }
+    int cur_dtype = dtype;
+    if (ix->whiten) {
+      int rc = ix->white.ensure((size_t)kStageRows * ix->dim * sizeof(float));
+      if (rc != LK_OK) return rc;
+      rc = launch_whiten(cur, dtype, cnt, ix->dim, ix->whiten, ix->white.as<float>(), st);
+      if (rc != LK_OK) return rc;
+      cur = ix->white.p;
+      cur_dtype = LK_F32;
+    }
+    int rc = launch_tile_rows(cur, cur_dtype, cnt, ix->g, tiles, side, row0 + done, ix->side_mode, ix->prenorm, st);
+    if (rc != LK_OK) return rc;
+    // the staging buffers are reused by the next step
+    if (done + cnt < n && mem == LK_HOST) LK_CUDA(cudaStreamSynchronize(st));
+  }
+  return LK_OK;
+}
+
+int lk_index_add(lk_index* ix, const void* rows, int dtype, int mem, int64_t n_rows, void* stream) {
+  if (!ix || (!rows && n_rows > 0) || n_rows < 0 || (dtype != LK_F32 && dtype != LK_BF16) ||
+      (mem != LK_HOST && mem != LK_DEVICE)) {
+    set_error("lk_index_add: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (ix->n_rows + n_rows > ix->capacity) {
+    set_error("lk_index_add: %lld + %lld rows exceed the capacity %lld", (long long)ix->n_rows,
+              (long long)n_rows, (long long)ix->capacity);
+    return LK_ERR_CAPACITY;
+  }
+  DeviceGuard guard(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ingest_rows(ix, rows, dtype, mem, n_rows, ix->tiles, ix->side, ix->n_rows, st);
+  if (rc != LK_OK) return rc;
+  if (mem == LK_HOST) LK_CUDA(cudaStreamSynchronize(st));  // the caller may free `rows` on return
+  ix->n_rows += n_rows;
+  return LK_OK;
+}
+
+int lk_index_reserve(lk_index* ix, int64_t capacity_rows) {
+  if (!ix || capacity_rows > 0x7fffff00LL) {
+    set_error("lk_index_reserve: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (capacity_rows <= ix->capacity) return LK_OK;
+  DeviceGuard guard(ix->device);
+  const int64_t old_blk = (ix->capacity + kBlockRows - 1) / kBlockRows;
+  const int64_t new_blk = (capacity_rows + kBlockRows - 1) / kBlockRows;
+  const size_t bb = (size_t)ix->g.block_bytes();
+  unsigned char* tiles = nullptr;
+  float* side = nullptr;
+  cudaError_t e = cudaMalloc((void**)&tiles, (size_t)new_blk * bb);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&side, (size_t)new_blk * kBlockRows * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(tiles, ix->tiles, (size_t)old_blk * bb, cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess) e = cudaMemset(tiles + (size_t)old_blk * bb, 0, (size_t)(new_blk - old_blk) * bb);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(side, ix->side, (size_t)old_blk * kBlockRows * sizeof(float), cudaMemcpyDeviceToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemset(side + (size_t)old_blk * kBlockRows, 0xFF, (size_t)(new_blk - old_blk) * kBlockRows * sizeof(float));
+  if (e != cudaSuccess) {
+    if (tiles) cudaFree(tiles);
+    if (side) cudaFree(side);
+    return cuda_fail(e, "lk_index_reserve", __FILE__, __LINE__);
+  }
+  cudaFree(ix->tiles);
+  cudaFree(ix->side);
+  ix->tiles = tiles;
+  ix->side = side;
+  ix->capacity = capacity_rows;
+  return LK_OK;
+}
+
+int lk_index_storage_bytes(const lk_index* ix, int64_t* out_tile_bytes, int64_t* out_side_bytes) {
+  if (!ix) return LK_ERR_INVALID;
+  const int64_t nblk = (ix->n_rows + kBlockRows - 1) / kBlockRows;
+  if (out_tile_bytes) *out_tile_bytes = nblk * ix->g.block_bytes();
+  if (out_side_bytes) *out_side_bytes = nblk * kBlockRows * (int64_t)sizeof(float);
+  return LK_OK;
+}
+
+int lk_index_export(lk_index* ix, void* tiles_host, void* side_host) {
+  if (!ix || !tiles_host || !side_host) return LK_ERR_INVALID;
+  DeviceGuard guard(ix->device);
+  int64_t tb = 0, sb = 0;
+  lk_index_storage_bytes(ix, &tb, &sb);
+  LK_CUDA(cudaMemcpy(tiles_host, ix->tiles, (size_t)tb, cudaMemcpyDeviceToHost));
+  LK_CUDA(cudaMemcpy(side_host, ix->side, (size_t)sb, cudaMemcpyDeviceToHost));
+  return LK_OK;
+}
+
+int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host, int64_t n_rows) {
+  if (!ix || !tiles_host || !side_host || n_rows < 0) return LK_ERR_INVALID;
+  if (ix->n_rows != 0) {
+    set_error("lk_index_import: the index is not empty");
+    return LK_ERR_INVALID;
+  }
+  if (n_rows > ix->capacity) {
+    set_error("lk_index_import: %lld rows exceed the capacity %lld", (long long)n_rows, (long long)ix->capacity);
+    return LK_ERR_CAPACITY;
+  }
+  DeviceGuard guard(ix->device);
+  const int64_t nblk = (n_rows + kBlockRows - 1) / kBlockRows;
+  LK_CUDA(cudaMemcpy(ix->tiles, tiles_host, (size_t)(nblk * ix->g.block_bytes()), cudaMemcpyHostToDevice));
+  LK_CUDA(cudaMemcpy(ix->side, side_host, (size_t)nblk * kBlockRows * sizeof(float), cudaMemcpyHostToDevice));
+  ix->n_rows = n_rows;
+  return LK_OK;
+}
+
+int lk_index_set_timing(lk_index* ix, int enabled) {
+  if (!ix) return LK_ERR_INVALID;
+  ix->timing = enabled != 0;
+  return LK_OK;
+}
+
+int lk_index_last_timing(lk_index* ix, float* out_search_kernel_ms, float* out_total_ms) {
+  if (!ix) return LK_ERR_INVALID;
+  if (out_search_kernel_ms) *out_search_kernel_ms = ix->last_search_ms;
+  if (out_total_ms) *out_total_ms = ix->last_total_ms;
+  return LK_OK;
+}
+
+static int pick_kernel(const lk_index* ix, int requested, int k) {
+  const char* env = getenv("LK_FORCE_KERNEL");
+  if (env && !strcmp(env, "simt")) requested = LK_KERNEL_SIMT;
+  if (env && !strcmp(env, "umma")) requested = LK_KERNEL_UMMA;
+  if (requested == LK_KERNEL_AUTO) return umma_supported(ix->g, k) ? LK_KERNEL_UMMA : LK_KERNEL_SIMT;
+  return requested;
+}
+
+int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, int64_t b, int k,
+                    float* out_scores, int64_t* out_idx, int out_mem, int64_t idx_base, int kernel,
+                    void* stream) {
+  if (!ix || b < 0 || (b > 0 && (!queries || !out_scores || !out_idx)) ||
+      (q_dtype != LK_F32 && q_dtype != LK_BF16) || (q_mem != LK_HOST && q_mem != LK_DEVICE) ||
+      (out_mem != LK_HOST && out_mem != LK_DEVICE)) {
+    set_error("lk_index_search: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (k < 1 || k > kMaxK) {
+    set_error("lk_index_search: k=%d outside 1..%d", k, kMaxK);
+    return LK_ERR_INVALID;
+  }
+  if (ix->n_rows < 1) {
+    set_error("lk_index_search: the index is empty");
+    return LK_ERR_INVALID;
+  }
+  if (b == 0) return LK_OK;
+  const int which = pick_kernel(ix, kernel, k);
+  if (which == LK_KERNEL_UMMA && !umma_supported(ix->g, k)) {
+    set_error("lk_index_search: the tcgen05 kernel needs bf16 storage and k <= 32 (k=%d, storage=%d)", k,
+              ix->storage);
+    return LK_ERR_UNSUPPORTED;
+  }
+  DeviceGuard guard(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+
+  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[0], st));
+
+  // 1. queries -> tiles (+ side values), same geometry and rounding as the corpus
+  const int64_t b_pad = round_up64(b, kBlockRows);
+  const size_t qt_bytes = (size_t)(b_pad / kBlockRows) * ix->g.block_bytes();
+  if ((rc = ix->q_tiles.ensure(qt_bytes)) != LK_OK) return rc;
+  if ((rc = ix->q_side.ensure((size_t)b_pad * sizeof(float))) != LK_OK) return rc;
+  LK_CUDA(cudaMemsetAsync(ix->q_tiles.p, 0, qt_bytes, st));
+  rc = ingest_rows(ix, queries, q_dtype, q_mem, b, ix->q_tiles.p, ix->q_side.as<float>(), 0, st);
+  if (rc != LK_OK) return rc;
+
+  // 2. plan + partial lists
+  SearchArgs a;
+  a.tiles = ix->tiles;
+  a.side = ix->side;
+  a.n_rows = ix->n_rows;
+  a.g = ix->g;
+  a.q_tiles = ix->q_tiles.p;
+  a.q_side = ix->q_side.as<float>();
+  a.n_queries = b;
+  a.metric = ix->kmetric;
+  a.k = k;
+  a.err_flag = ix->err_flag;
+  if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
+  else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
+  if (rc != LK_OK) return rc;
+  const size_t n_part = (size_t)b * a.n_lists * a.ksel;
+  if ((rc = ix->part_s.ensure(n_part * sizeof(float))) != LK_OK) return rc;
+  if ((rc = ix->part_i.ensure(n_part * sizeof(int32_t))) != LK_OK) return rc;
+  a.part_scores = ix->part_s.as<float>();
+  a.part_idx = ix->part_i.as<int32_t>();
+  LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
+  LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
+
+  // 3. fused distance + selection
+  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
+  if (which == LK_KERNEL_UMMA) rc = launch_search_umma(a, ix->sm_count, st);
+  else rc = launch_search_simt(a, ix->sm_count, st);
+  if (rc != LK_OK) return rc;
+  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[2], st));
+
+  // 4. merge the per-CTA lists
+  float* d_s = out_scores;
+  int64_t* d_i = out_idx;
+  if (out_mem == LK_HOST) {
+    if ((rc = ix->out_s.ensure((size_t)b * k * sizeof(float))) != LK_OK) return rc;
+    if ((rc = ix->out_i.ensure((size_t)b * k * sizeof(int64_t))) != LK_OK) return rc;
+    d_s = ix->out_s.as<float>();
+    d_i = ix->out_i.as<int64_t>();
+  }
+  rc = launch_merge_i32(a.part_scores, a.part_idx, b, a.n_lists, a.ksel, k, idx_base, d_s, d_i, st);
+  if (rc != LK_OK) return rc;
+  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[3], st));
+
+  // 5. results (and the kernels' error flag) back to the host
+  if (out_mem == LK_HOST) {
+    int flag = 0;
+    LK_CUDA(cudaMemcpyAsync(out_scores, d_s, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaMemcpyAsync(out_idx, d_i, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaMemcpyAsync(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaStreamSynchronize(st));
+    if (flag != 0) {
+      cudaMemsetAsync(ix->err_flag, 0, sizeof(int), st);
+      set_error("search kernel pipeline timed out (barrier code %d); results are invalid", flag);
+      return LK_ERR_CUDA;
+    }
+  }
+  if (ix->timing) {
+    LK_CUDA(cudaEventSynchronize(ix->ev[3]));
+    LK_CUDA(cudaEventElapsedTime(&ix->last_search_ms, ix->ev[1], ix->ev[2]));
+    LK_CUDA(cudaEventElapsedTime(&ix->last_total_ms, ix->ev[0], ix->ev[3]));
+    if (out_mem == LK_DEVICE) {
+      int flag = 0;
+      LK_CUDA(cudaMemcpy(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+      if (flag != 0) {
+        cudaMemset(ix->err_flag, 0, sizeof(int));
+        set_error("search kernel pipeline timed out (barrier code %d); results are invalid", flag);
+        return LK_ERR_CUDA;
+      }
+    }
+  }
+  return LK_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// merge of per-shard candidates
+// ------------------------------------------------------------------------------------
+int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b, int n_lists,
+                  int list_len, int k, float* out_scores, int64_t* out_idx, int mem, void* stream) {
+  if (b < 0 || n_lists < 1 || list_len < 1 || k < 1 || k > kMaxK || (mem != LK_HOST && mem != LK_DEVICE) ||
+      (b > 0 && (!cand_scores || !cand_idx || !out_scores || !out_idx))) {
+    set_error("lk_merge_topk: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (b == 0) return LK_OK;
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc != LK_OK) return rc;
+  DeviceGuard guard(device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mem == LK_DEVICE) return launch_merge_i64(cand_scores, cand_idx, b, n_lists, list_len, k, out_scores, out_idx, st);
+  const size_t nc = (size_t)b * n_lists * list_len, no = (size_t)b * k;
+  Buf cs, ci, os, oi;
+  auto done = [&](int code) {
+    cs.release(); ci.release(); os.release(); oi.release();
+    return code;
+  };
+  if ((rc = cs.ensure(nc * 4)) != LK_OK || (rc = ci.ensure(nc * 8)) != LK_OK ||
+      (rc = os.ensure(no * 4)) != LK_OK || (rc = oi.ensure(no * 8)) != LK_OK)
+    return done(rc);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(cs.p, cand_scores, nc * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(ci.p, cand_idx, nc * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return done(cuda_fail(e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__));
+  rc = launch_merge_i64(cs.as<float>(), ci.as<int64_t>(), b, n_lists, list_len, k, os.as<float>(),
+                        oi.as<int64_t>(), st);
+  if (rc != LK_OK) return done(rc);
+  if ((e = cudaMemcpyAsync(out_scores, os.p, no * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(out_idx, oi.p, no * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(st)) != cudaSuccess)
+    return done(cuda_fail(e, "merge D2H", __FILE__, __LINE__));
+  return done(LK_OK);
+}
+
+// ------------------------------------------------------------------------------------
+// autoencoder encoder
+// ------------------------------------------------------------------------------------
+int lk_ae_destroy(lk_ae* ae) {
+  if (!ae) return LK_OK;
+  DeviceGuard guard(ae->device);
+  float* ps[] = {ae->w0t, ae->b0, ae->w1t, ae->b1};
+  for (float* p : ps)
+    if (p) cudaFree(p);
+  ae->xin.release();
+  ae->zout.release();
+  delete ae;
+  return LK_OK;
+}
+
+int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int d_latent, const float* w0,
+                 const float* b0, const float* w1, const float* b1) {
+  if (!out) return LK_ERR_INVALID;
+  *out = nullptr;
+  if (kind < LK_AE_DAE || kind > LK_AE_VAE_MU || d_in < 1 || d_hidden < 1 || d_latent < 1 || !w0 || !b0 ||
+      !w1 || !b1) {
+    set_error("lk_ae_create: bad argument");
+    return LK_ERR_INVALID;
+  }
+  int sm = 0;
+  int rc = check_device(device, &sm);
+  if (rc != LK_OK) return rc;
+  DeviceGuard guard(device);
+  lk_ae* ae = new (std::nothrow) lk_ae();
+  if (!ae) return LK_ERR_OOM;
+  ae->device = device;
+  ae->kind = kind;
+  ae->d_in = d_in;
+  ae->d_hidden = d_hidden;
+  ae->d_latent = d_latent;
+  // nn.Linear keeps [out, in]; the kernel wants [in, out] so that threads of a warp read
+  // consecutive output columns
+  std::vector<float> w0t((size_t)d_in * d_hidden), w1t((size_t)d_hidden * d_latent);
+  for (int o = 0; o < d_hidden; ++o)
+    for (int i = 0; i < d_in; ++i) w0t[(size_t)i * d_hidden + o] = w0[(size_t)o * d_in + i];
+  for (int o = 0; o < d_latent; ++o)
+    for (int i = 0; i < d_hidden; ++i) w1t[(size_t)i * d_latent + o] = w1[(size_t)o * d_hidden + i];
+  struct Up { float** dst; const float* src; size_t n; } ups[] = {
+      {&ae->w0t, w0t.data(), w0t.size()}, {&ae->b0, b0, (size_t)d_hidden},
+      {&ae->w1t, w1t.data(), w1t.size()}, {&ae->b1, b1, (size_t)d_latent}};
+  for (auto& u : ups) {
+    cudaError_t e = cudaMalloc((void**)u.dst, u.n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(*u.dst, u.src, u.n * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "ae weight upload", __FILE__, __LINE__);
+      lk_ae_destroy(ae);
+      return rc;
+    }
+  }
+  *out = ae;
+  return LK_OK;
+}
+
+int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream) {
+  if (!ae || m < 0 || (m > 0 && (!x || !z)) || (x_mem != LK_HOST && x_mem != LK_DEVICE) ||
+      (z_mem != LK_HOST && z_mem != LK_DEVICE)) {
+    set_error("lk_ae_encode: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (m == 0) return LK_OK;
+  DeviceGuard guard(ae->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int l2 = ae->kind == LK_AE_CAE ? 1 : 0;
+  const int64_t step = 1 << 18;
+  int rc;
+  for (int64_t done = 0; done < m; done += step) {
+    const int64_t cnt = m - done < step ? m - done : step;
+    const float* xin = x + (size_t)done * ae->d_in;
+    float* zo = z + (size_t)done * ae->d_latent;
+    if (x_mem == LK_HOST) {
+      if ((rc = ae->xin.ensure((size_t)step * ae->d_in * 4)) != LK_OK) return rc;
+      LK_CUDA(cudaMemcpyAsync(ae->xin.p, xin, (size_t)cnt * ae->d_in * 4, cudaMemcpyHostToDevice, st));
+      xin = ae->xin.as<float>();
+    }
+    float* zdev = zo;
+    if (z_mem == LK_HOST) {
+      if ((rc = ae->zout.ensure((size_t)step * ae->d_latent * 4)) != LK_OK) return rc;
+      zdev = ae->zout.as<float>();
+    }
+    rc = launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1,
+                          l2, zdev, st);
+    if (rc != LK_OK) return rc;
+    if (z_mem == LK_HOST)
+      LK_CUDA(cudaMemcpyAsync(zo, zdev, (size_t)cnt * ae->d_latent * 4, cudaMemcpyDeviceToHost, st));
+    if (x_mem == LK_HOST || z_mem == LK_HOST) LK_CUDA(cudaStreamSynchronize(st));
+  }
+  return LK_OK;
+}
+
+}  // extern "C"

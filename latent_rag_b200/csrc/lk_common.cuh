@@ -1,0 +1,117 @@
+// Internal declarations shared by the liblatentknn translation units (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "latentknn.h"
+
+namespace lk {
+
+// ---------------------------------------------------------------------------------
+// Data layout in HBM (DESIGN.md "Data layout")
+//
+// The corpus is stored as ROW BLOCKS of 128 rows.  Inside a block the bytes are the
+// tcgen05 "K-major, no-swizzle" canonical operand image:
+//
+//     block[kc][r][16 bytes]      kc = 16-byte K chunk (8 bf16 or 4 fp32), r = 0..127
+//
+// so that (a) one 16 KB cp.async.bulk brings a [128 rows x 64 K] bf16 operand slab into
+// shared memory ready for tcgen05.mma (core matrix = 8 rows x 16 B contiguous,
+// SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks), and (b) a SIMT warp
+// reading "its" rows for one kc touches 512 contiguous bytes.
+// ---------------------------------------------------------------------------------
+constexpr int kBlockRows = 128;       // rows per row block (= UMMA M / N granule)
+constexpr int kChunkBytes = 16;       // one K chunk of one row
+constexpr int kKBlockElems = 64;      // bf16 elements per pipeline K block
+constexpr int kMaxK = 128;            // largest supported top-k
+constexpr int kSimtQG = 4;            // queries per CTA pass in the SIMT kernel
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// (score, index) total order used everywhere a choice between candidates is made:
+// higher score first, lower index on equal scores.  Makes results independent of how
+// the corpus is partitioned over CTAs / GPUs.
+__device__ __forceinline__ bool better(float sa, int64_t ia, float sb, int64_t ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// ---------------------------------------------------------------------------------
+// error plumbing (host)
+// ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define LK_CUDA(expr)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return ::lk::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define LK_CHECK_LAUNCH(name)                                                \
+  do {                                                                       \
+    ::lk::count_launch();                                                    \
+    cudaError_t _e = cudaGetLastError();                                     \
+    if (_e != cudaSuccess) return ::lk::cuda_fail(_e, name, __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// kernel launchers (defined in the .cu files, called from lk_api.cu)
+// ---------------------------------------------------------------------------------
+struct TileGeom {
+  int dim;          // logical dimension
+  int dim_pad;      // padded to a multiple of 64 elements (bf16) / 64 (fp32)
+  int elem_bytes;   // 2 (bf16) or 4 (fp32)
+  int chunks;       // dim_pad * elem_bytes / 16
+  __host__ __device__ int64_t block_bytes() const { return (int64_t)chunks * kBlockRows * kChunkBytes; }
+};
+
+// rows [n, dim] (fp32 or bf16 row-major, device) -> tiled storage starting at row
+// `row0`, plus one fp32 side value per row.  side_mode: 0 = 1/max(|row|,1e-12) of the
+// stored values, 1 = |row|^2 of the stored values.  prenorm: divide the row by
+// max(|row|, 1e-12) before storing (fp32 cosine storage, like F.normalize).
+int launch_tile_rows(const void* rows, int rows_dtype, int64_t n, const TileGeom& g, void* tiles,
+                     float* side, int64_t row0, int side_mode, int prenorm, cudaStream_t st);
+
+// out[n, dim] fp32 = rows[n, dim] (fp32 or bf16) * L[dim, dim] (fp64, row-major), fp64 accumulate
+int launch_whiten(const void* rows, int rows_dtype, int64_t n, int dim, const double* L, float* out,
+                  cudaStream_t st);
+
+struct SearchArgs {
+  const void* tiles;       // corpus tiles
+  const float* side;       // per-row side value (NaN for rows past the end)
+  int64_t n_rows;
+  TileGeom g;
+  const void* q_tiles;     // query tiles (same layout, 128 queries per block)
+  const float* q_side;
+  int64_t n_queries;
+  int metric;              // LK_COSINE or LK_EUCLIDEAN (mahalanobis is whitened L2)
+  int k;                   // requested k
+  int ksel;                // entries per partial list (>= k)
+  int n_lists;             // partial lists per query (stride of the partial arrays)
+  float* part_scores;      // [n_queries, n_lists, ksel]
+  int32_t* part_idx;       // [n_queries, n_lists, ksel]
+  int* err_flag;           // device int, set non-zero by a kernel that timed out
+};
+
+int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
+int launch_search_simt(const SearchArgs& a, int sm_count, cudaStream_t st);
+int umma_supported(const TileGeom& g, int k);
+int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
+int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st);
+
+// merge [b, n_lists, list_len] candidates -> [b, k]; idx type int32 (+base) or int64
+int launch_merge_i32(const float* ps, const int32_t* pi, int64_t b, int n_lists, int list_len, int k,
+                     int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st);
+int launch_merge_i64(const float* ps, const int64_t* pi, int64_t b, int n_lists, int list_len, int k,
+                     float* out_s, int64_t* out_i, cudaStream_t st);
+
+int launch_ae_encode(const float* x, int64_t m, int d_in, int d_hidden, int d_latent, const float* w0t,
+                     const float* b0, const float* w1t, const float* b1, int l2norm, float* z,
+                     cudaStream_t st);
+
+}  // namespace lk

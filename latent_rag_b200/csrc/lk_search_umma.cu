@@ -1,0 +1,430 @@
+// Fused distance + top-k selection on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces retrieval/bruteforce.py:66-82 of the reference (`q @ emb.T`, the euclidean
+// expansion, `torch.topk`) and IndexFlatIP.search behind
+// retrieval/FAISSEmbeddingRetriever.py:322 with ONE kernel in which the [B, N] score
+// matrix only ever exists as 128x128 fp32 tiles in tensor memory.
+//
+// Shape of the computation
+//   unit       = (query tile of 128 queries) x (row block of 128 corpus rows)
+//   D[q][row]  = sum_k Q[q][k] * E[row][k]       tcgen05.mma M=128 (queries -> TMEM lanes)
+//                                                 N=128 (rows -> TMEM columns), K=16/instr
+//   CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G) of the query-tile-major unit
+//   order, so a CTA changes query tile at most once when there are <= G query tiles and
+//   CTAs whose ranges start at the same corpus offset share the row blocks through L2.
+//
+// Warp roles (384 threads, 1 CTA / SM)
+//   warp 0      TMA producer: 16 KB cp.async.bulk per (row block, K block of 64) into a
+//               ring of shared-memory stages; also brings the query tile in
+//   warp 1      MMA issuer (one thread): 4 tcgen05.mma per K block, accumulating a unit
+//               in one of 4 TMEM stages of 128 columns; tcgen05.commit frees smem stages
+//               and publishes finished accumulators
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: TMEM lane = query, so each thread owns ONE query (for half of
+//               the columns) and keeps its running top-k in registers: tcgen05.ld 32
+//               columns, apply the metric (cosine norm / L2 expansion) with the per-row
+//               side value, compare against the k-th best, insert on the rare hit.
+//
+// The operand images in HBM are already in the tcgen05 canonical K-major no-swizzle
+// layout (lk_common.cuh), so the producer needs no tensor map: every copy is a
+// contiguous 16 KB UBLKCP.
+#include "lk_ptx.cuh"
+#include "lk_topk.cuh"
+
+namespace lk {
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kColSplit = kEpiWarps / 4;                 // epilogue warps per lane quarter
+constexpr int kColsPerWarp = kBlockRows / kColSplit;     // 64 columns of each accumulator
+constexpr int kAccStages = 4;                            // 4 x 128 columns = all of TMEM
+constexpr int kTmemCols = kAccStages * kBlockRows;       // 512
+constexpr int kKBlockBytes = kBlockRows * kKBlockElems * 2;  // 16384
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kHeaderBytes = 256 + kEpiWarps * 2 * kColsPerWarp * 4;  // barriers + side rings
+constexpr uint32_t kLbo = kBlockRows * kChunkBytes;      // 2048: next K chunk
+constexpr uint32_t kSbo = 8 * kChunkBytes;               // 128 : next 8-row group
+
+enum UmmaErr {
+  kErrProdEmpty = 101, kErrProdQEmpty = 102, kErrMmaFull = 103, kErrMmaTmemEmpty = 104,
+  kErrMmaQFull = 105, kErrEpiTmemFull = 106
+};
+
+struct UmmaParams {
+  const unsigned char* tiles;
+  const float* side;
+  const unsigned char* q_tiles;
+  const float* q_side;
+  int64_t n_queries;
+  int64_t total_units;   // n_qt * nblk
+  int nblk;              // row blocks in the corpus
+  int nkb;               // K blocks of 64 per row
+  int n_stages;
+  int n_lists;
+  int64_t block_bytes;
+  float* part_scores;    // [n_queries, n_lists, KSEL]
+  int32_t* part_idx;
+  int* err_flag;
+  uint32_t lbo, sbo;
+};
+
+__host__ __device__ inline int64_t unit_begin(int64_t c, int64_t total, int64_t grid) {
+  return c * total / grid;
+}
+// the CTA whose range contains unit u
+__host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t total, int64_t grid) {
+  return ((u + 1) * grid - 1) / total;
+}
+
+struct Ring {
+  int idx = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) {
+      idx = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+template <int KSEL, int METRIC, bool QRES>
+__global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // barrier slots: full[8] empty[8] tfull[4] tempty[4] qfull qempty
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + kAccStages + s); };
+  const uint32_t qfull_bar = bar0 + 8u * (2 * kMaxStages + 2 * kAccStages);
+  const uint32_t qempty_bar = qfull_bar + 8u;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + 240);
+  volatile int* abort_s = reinterpret_cast<volatile int*>(smem + 244);
+  float* side_ring = reinterpret_cast<float*>(smem + 256);
+  unsigned char* q_sm = smem + kHeaderBytes;
+  unsigned char* stage_sm = q_sm + (QRES ? p.nkb * kKBlockBytes : 0);
+  constexpr int kStageBytes = QRES ? kKBlockBytes : 2 * kKBlockBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t G = gridDim.x, c = blockIdx.x;
+  const int64_t u0 = unit_begin(c, p.total_units, G), u1 = unit_begin(c + 1, p.total_units, G);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), kEpiWarps);
+    }
+    ptx::mbar_init(qfull_bar, 1);
+    ptx::mbar_init(qempty_bar, 1);
+    *abort_s = 0;
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  auto fail = [&](int code) {
+    atomicCAS(p.err_flag, 0, code);
+    *abort_s = 1;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      Ring st;
+      int seg = 0;
+      int64_t u = u0;
+      int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
+      bool ok = true;
+      for (; u < u1 && ok; ++u) {
+        const unsigned char* q_src = p.q_tiles + (int64_t)qt * p.block_bytes;
+        if (QRES && (u == u0 || b == 0)) {
+          if (seg > 0 && !ptx::mbar_wait(qempty_bar, (uint32_t)((seg - 1) & 1))) {
+            fail(kErrProdQEmpty);
+            break;
+          }
+          ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(p.nkb * kKBlockBytes));
+          for (int kb = 0; kb < p.nkb; ++kb)
+            ptx::bulk_g2s(ptx::smem_u32(q_sm + kb * kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
+                          kKBlockBytes, qfull_bar);
+          ++seg;
+        }
+        const unsigned char* e_src = p.tiles + (int64_t)b * p.block_bytes;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (!ptx::mbar_wait(empty_bar(st.idx), st.phase ^ 1u)) {
+            fail(kErrProdEmpty);
+            ok = false;
+            break;
+          }
+          unsigned char* dst = stage_sm + st.idx * kStageBytes;
+          ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
+          ptx::bulk_g2s(ptx::smem_u32(dst), e_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
+                        full_bar(st.idx));
+          if (!QRES)
+            ptx::bulk_g2s(ptx::smem_u32(dst + kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
+                          kKBlockBytes, full_bar(st.idx));
+          st.advance(p.n_stages);
+        }
+        if (++b == p.nblk) {
+          b = 0;
+          ++qt;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockRows, kBlockRows);
+      Ring st, acc;
+      int seg = 0;
+      int b = (int)(u0 % p.nblk);
+      bool ok = true;
+      for (int64_t u = u0; u < u1 && ok; ++u) {
+        if (!ptx::mbar_wait(tempty_bar(acc.idx), acc.phase ^ 1u)) {
+          fail(kErrMmaTmemEmpty);
+          break;
+        }
+        if (QRES && (u == u0 || b == 0)) {
+          if (!ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1))) {
+            fail(kErrMmaQFull);
+            break;
+          }
+          ++seg;
+        }
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc.idx * kBlockRows);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          if (!ptx::mbar_wait(full_bar(st.idx), st.phase)) {
+            fail(kErrMmaFull);
+            ok = false;
+            break;
+          }
+          ptx::tc_fence_after();
+          const uint32_t e_addr = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
+          const uint32_t q_addr = QRES ? ptx::smem_u32(q_sm + kb * kKBlockBytes) : e_addr + kKBlockBytes;
+#pragma unroll
+          for (int k = 0; k < kKBlockElems / 16; ++k) {
+            const uint32_t off = (uint32_t)k * 2u * kLbo;  // 16 K elements = 2 chunks
+            ptx::umma_bf16(d_tmem, ptx::smem_desc(q_addr + off, p.lbo, p.sbo),
+                           ptx::smem_desc(e_addr + off, p.lbo, p.sbo), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(st.idx));  // smem stage reusable once these MMAs retire
+          st.advance(p.n_stages);
+        }
+        if (!ok) break;
+        ptx::umma_commit(tfull_bar(acc.idx));   // accumulator complete -> epilogue
+        acc.advance(kAccStages);
+        const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
+        if (QRES && seg_end) ptx::umma_commit(qempty_bar);  // query tile no longer read
+        if (++b == p.nblk) b = 0;
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ===================== epilogue: metric + running top-k =====================
+    const int ew = warp - kFirstEpiWarp;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int ch = ew >> 2;                  // which half of the 128 columns
+    const int lane_q = quarter * 32 + lane;  // query within the tile
+    float* my_side = side_ring + ew * (2 * kColsPerWarp);
+    Ring acc;
+    int slot = 0;
+    int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
+    RegTopK<KSEL> top;
+    top.init();
+    float thr = top.threshold();
+    float q_sd = 0.f;
+    bool seg_start = true;
+    if (u0 < u1) {
+      const float* sp = p.side + (int64_t)b * kBlockRows + ch * kColsPerWarp;
+      my_side[lane] = sp[lane];
+      my_side[lane + 32] = sp[lane + 32];
+      __syncwarp();
+    }
+    for (int64_t u = u0; u < u1; ++u) {
+      if (seg_start) {
+        const int64_t q = (int64_t)qt * kBlockRows + lane_q;
+        q_sd = q < p.n_queries ? p.q_side[q] : 0.f;
+        top.init();
+        thr = top.threshold();
+        seg_start = false;
+      }
+      // prefetch the next unit's side values while this unit's MMAs finish
+      int nb = b + 1, nqt = qt;
+      if (nb == p.nblk) {
+        nb = 0;
+        ++nqt;
+      }
+      float ns0 = 0.f, ns1 = 0.f;
+      if (u + 1 < u1) {
+        const float* sp = p.side + (int64_t)nb * kBlockRows + ch * kColsPerWarp;
+        ns0 = sp[lane];
+        ns1 = sp[lane + 32];
+      }
+      if (!ptx::mbar_wait(tfull_bar(acc.idx), acc.phase)) {
+        if (lane == 0) fail(kErrEpiTmemFull);
+        break;
+      }
+      ptx::tc_fence_after();
+      const float* sd = my_side + slot * kColsPerWarp;
+      const int32_t row0 = b * kBlockRows + ch * kColsPerWarp;
+#pragma unroll
+      for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)(acc.idx * kBlockRows + ch * kColsPerWarp + chunk * 32);
+        ptx::tmem_ld32(taddr, r);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dot = __uint_as_float(r[j]);
+          const float e_sd = sd[chunk * 32 + j];
+          float s;
+          if (METRIC == LK_COSINE) s = dot * e_sd;                 // x 1/|e|; x 1/|q| at flush
+          else s = fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
+          if (s > thr) {                                           // NaN (padding rows) never passes
+            top.insert(s, row0 + chunk * 32 + j);
+            thr = top.threshold();
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc.idx));
+      acc.advance(kAccStages);
+      slot ^= 1;
+      my_side[slot * kColsPerWarp + lane] = ns0;
+      my_side[slot * kColsPerWarp + lane + 32] = ns1;
+      __syncwarp();
+
+      const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
+      if (seg_end) {
+        const int64_t q = (int64_t)qt * kBlockRows + lane_q;
+        if (q < p.n_queries) {
+          const int64_t c_first = cta_of_unit((int64_t)qt * p.nblk, p.total_units, G);
+          const int list = (int)(c - c_first) * kColSplit + ch;
+          const int64_t o = (q * p.n_lists + list) * KSEL;
+#pragma unroll
+          for (int j = 0; j < KSEL; ++j) {
+            p.part_scores[o + j] = METRIC == LK_COSINE ? top.s[j] * q_sd : top.s[j];
+            p.part_idx[o + j] = top.ix[j];
+          }
+        }
+        seg_start = true;
+      }
+      b = nb;
+      qt = nqt;
+    }
+  }
+
+  // ===================== teardown =====================
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+inline int n_kblocks(const TileGeom& g) { return g.dim_pad / kKBlockElems; }
+inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
+inline int n_stages_for(const TileGeom& g) {
+  const int stage = q_resident(g) ? kKBlockBytes : 2 * kKBlockBytes;
+  const int q_bytes = q_resident(g) ? n_kblocks(g) * kKBlockBytes : 0;
+  int s = (kSmemBudget - kHeaderBytes - q_bytes) / stage;
+  return s > kMaxStages ? kMaxStages : s;
+}
+inline int ksel_for(int k) { return k <= 10 ? 10 : 32; }
+
+}  // namespace
+
+int umma_supported(const TileGeom& g, int k) {
+  return g.elem_bytes == 2 && g.dim_pad % kKBlockElems == 0 && k >= 1 && k <= 32 && n_stages_for(g) >= 2;
+}
+
+int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
+  const int64_t nblk = (a.n_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
+  const int64_t total = nblk * nqt;
+  const int64_t grid = total < sm_count ? total : sm_count;
+  int64_t maxc = 1;
+  for (int64_t qt = 0; qt < nqt; ++qt) {
+    const int64_t cf = cta_of_unit(qt * nblk, total, grid), cl = cta_of_unit((qt + 1) * nblk - 1, total, grid);
+    if (cl - cf + 1 > maxc) maxc = cl - cf + 1;
+  }
+  *n_lists = (int)maxc * kColSplit;
+  *ksel = ksel_for(a.k);
+  return LK_OK;
+}
+
+int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
+  if (a.n_queries <= 0 || a.n_rows <= 0) return LK_OK;
+  if (!umma_supported(a.g, a.k)) {
+    set_error("tcgen05 search: unsupported shape (dim_pad=%d, k=%d)", a.g.dim_pad, a.k);
+    return LK_ERR_UNSUPPORTED;
+  }
+  const int64_t nblk = (a.n_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
+  UmmaParams p;
+  p.tiles = static_cast<const unsigned char*>(a.tiles);
+  p.side = a.side;
+  p.q_tiles = static_cast<const unsigned char*>(a.q_tiles);
+  p.q_side = a.q_side;
+  p.n_queries = a.n_queries;
+  p.total_units = nblk * nqt;
+  p.nblk = (int)nblk;
+  p.nkb = n_kblocks(a.g);
+  p.n_stages = n_stages_for(a.g);
+  p.n_lists = a.n_lists;
+  p.block_bytes = a.g.block_bytes();
+  p.part_scores = a.part_scores;
+  p.part_idx = a.part_idx;
+  p.err_flag = a.err_flag;
+  p.lbo = kLbo;
+  p.sbo = kSbo;
+  const bool qres = q_resident(a.g);
+  const int stage = qres ? kKBlockBytes : 2 * kKBlockBytes;
+  const size_t smem = (size_t)kHeaderBytes + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
+                      (size_t)p.n_stages * stage;
+  const int64_t grid = p.total_units < sm_count ? p.total_units : sm_count;
+  const int ksel = ksel_for(a.k);
+  if (ksel != a.ksel) {
+    set_error("tcgen05 search: plan mismatch (ksel %d vs %d)", a.ksel, ksel);
+    return LK_ERR_INVALID;
+  }
+#define LK_UMMA(KS, MET, QR)                                                                         \
+  do {                                                                                               \
+    LK_CUDA(cudaFuncSetAttribute(umma_search_kernel<KS, MET, QR>,                                    \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    umma_search_kernel<KS, MET, QR><<<(unsigned)grid, kThreads, smem, st>>>(p);                      \
+  } while (0)
+#define LK_UMMA_M(KS, QR)                                                  \
+  do {                                                                     \
+    if (a.metric == LK_COSINE) LK_UMMA(KS, LK_COSINE, QR);                 \
+    else LK_UMMA(KS, LK_EUCLIDEAN, QR);                                    \
+  } while (0)
+  if (ksel == 10) {
+    if (qres) LK_UMMA_M(10, true); else LK_UMMA_M(10, false);
+  } else {
+    if (qres) LK_UMMA_M(32, true); else LK_UMMA_M(32, false);
+  }
+#undef LK_UMMA_M
+#undef LK_UMMA
+  LK_CHECK_LAUNCH("umma_search_kernel");
+  return LK_OK;
+}
+
+}  // namespace lk

@@ -161,6 +161,8 @@ def shard_bounds(n: int, world: int) -> Sequence[Tuple[int, int]]:
 def merge_topk(cand_d: np.ndarray, cand_i: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
     """Merge `[B, L]` candidate (score, global index) lists into the top-k, best first,
     ties by lower index; candidates with index < 0 are padding."""
+    cand_d = np.asarray(cand_d).reshape(len(cand_d), -1)  # [B, L] or [B, lists, len]
+    cand_i = np.asarray(cand_i).reshape(len(cand_i), -1)
     d = np.where(cand_i < 0, -np.inf, cand_d.astype(np.float32))
     order = np.lexsort((cand_i, -d), axis=1)[:, :k]
     return np.take_along_axis(d, order, 1).astype(np.float32), np.take_along_axis(cand_i, order, 1)

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: stats, error conventions, fingerprints, and the rule
+that the product fails loudly (never falls back) without a device."""
+import numpy as np
+import pytest
+import torch
+
+import latent_rag_b200 as lrb
+from latent_rag_b200 import _native
+from latent_rag_b200.retrieval.common import StatsTracker, empirical_precision, whitener_from_precision
+from latent_rag_b200.retrieval.FAISSEmbeddingRetriever import FAISSEmbeddingRetriever
+
+NO_GPU = not torch.cuda.is_available()
+
+
+def test_stats_tracker_contract():
+    """retrieval/common.py:37-65 of the reference."""
+    s = StatsTracker()
+    s.add_build_time(0.5)
+    s.add_search_batch(batch_size=4, seconds=0.2)
+    s.add_search_batch(batch_size=0, seconds=0.1)
+    out = s.get_stats()
+    assert set(out) == {"build_time_s", "search_time_s", "search_calls", "per_query_ms"}
+    assert out["build_time_s"] == 0.5 and out["search_calls"] == 2
+    assert abs(out["search_time_s"] - 0.3) < 1e-12
+    assert out["per_query_ms"] == [50.0, 100.0]
+    s.get_stats(reset=True)
+    assert s.get_stats() == {"build_time_s": 0.0, "search_time_s": 0.0, "search_calls": 0, "per_query_ms": []}
+
+
+def test_len_mismatch_is_an_assertion_error():
+    """test/test_retrieval.py:122-128 of the reference."""
+    emb = torch.randn(10, 8)
+    with pytest.raises(AssertionError):
+        lrb.BruteForceRetriever(emb, ["a"] * 10, doc_ids=[0, 1])
+
+
+def test_unsupported_metric_is_a_value_error():
+    with pytest.raises(ValueError, match="Unsupported metric"):
+        lrb.BruteForceRetriever(torch.randn(4, 8), ["a"] * 4, None, metric="manhattan")
+
+
+@pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_a_device():
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        lrb.ExactIndex(8, 16)
+    with pytest.raises(_native.NativeError):
+        lrb.merge_topk(np.zeros((1, 2, 3), np.float32), np.zeros((1, 2, 3), np.int64), 2)
+    ae = lrb.DenoisingAutoencoder(8, 2, 4)
+    ae.load_state_dict({"encoder.0.weight": np.zeros((4, 8)), "encoder.0.bias": np.zeros(4),
+                        "encoder.2.weight": np.zeros((2, 4)), "encoder.2.bias": np.zeros(2)})
+    with pytest.raises(_native.NativeError):
+        ae.encode(torch.zeros(3, 8))
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+
+    pkg = os.path.dirname(lrb.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_fingerprint_and_compat_rules():
+    """FAISSEmbeddingRetriever.py:139-179 of the reference."""
+    fp = FAISSEmbeddingRetriever._fingerprint(d=64, embedding_model="m", ae_type="vae", latent_dim=64,
+                                              chunking_cfg={"enabled": True, "max_tokens": 128})
+    assert fp["metric"] == "ip" and fp["normalize_l2"] is True and fp["version"] == 1
+    # absent keys stay None in the reference (`... if ch.get(key) is not None else None`)
+    assert fp["chunking"] == {"enabled": True, "mode": "sliding", "max_tokens": 128, "stride": None,
+                              "min_tokens": None}
+    r = FAISSEmbeddingRetriever.__new__(FAISSEmbeddingRetriever)
+    r.meta_fp = fp
+    assert r._compatible(dict(fp))
+    other = dict(fp, ae_type="dae")
+    assert not r._compatible(other)
+    other = dict(fp, chunking=dict(fp["chunking"], stride=32))
+    assert not r._compatible(other)
+
+
+def test_autoencoder_state_dict_contract():
+    ae = lrb.VariationalAutoencoder(16, 4, 8)
+    with pytest.raises(KeyError):
+        ae.load_state_dict({"encoder.0.weight": np.zeros((8, 16))})
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        ae.load_state_dict({"encoder.0.weight": np.zeros((8, 15)), "encoder.0.bias": np.zeros(8),
+                            "mu_layer.weight": np.zeros((4, 8)), "mu_layer.bias": np.zeros(4)})
+    with pytest.raises(ValueError):
+        lrb.load_autoencoder("gan", {})
+    with pytest.raises(FileNotFoundError):
+        lrb.load_autoencoder("vae", "/nonexistent/ckpt.pth")
+
+
+def test_empirical_precision_matches_oracle():
+    import oracle
+
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((300, 12)).astype(np.float32) * np.linspace(0.5, 2, 12, dtype=np.float32))
+    p = empirical_precision(x, chunk=64)
+    np.testing.assert_allclose(p, oracle.mahalanobis_precision(x), rtol=1e-8, atol=1e-10)
+    lw = whitener_from_precision(p)
+    np.testing.assert_allclose(lw @ lw.T, p, rtol=1e-9, atol=1e-10)
+
+
+def test_shard_bounds():
+    import oracle
+
+    for n, w in [(10, 3), (1000, 8), (7, 8), (0, 2), (128, 1)]:
+        b = lrb.shard_bounds(n, w)
+        assert b == list(oracle.shard_bounds(n, w))
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
