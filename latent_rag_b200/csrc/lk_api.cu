@@ -118,7 +118,7 @@ struct lk_index {
   float* side = nullptr;
   double* whiten = nullptr;
   int* err_flag = nullptr;
-  Buf stage, white, q_tiles, q_side, part_s, part_i, out_s, out_i;
+  Buf stage, white, q_tiles, q_side, part_s, part_i, out_s, out_i, debug;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_search_ms = 0.f, last_total_ms = 0.f;
@@ -157,7 +157,7 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->side) cudaFree(ix->side);
   if (ix->whiten) cudaFree(ix->whiten);
   if (ix->err_flag) cudaFree(ix->err_flag);
-  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->out_s, &ix->out_i};
+  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->out_s, &ix->out_i, &ix->debug};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : ix->ev)
     if (e) cudaEventDestroy(e);
@@ -431,6 +431,13 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   a.metric = ix->kmetric;
   a.k = k;
   a.err_flag = ix->err_flag;
+  a.debug_tile = nullptr;
+  const char* dump_path = which == LK_KERNEL_UMMA ? getenv("LK_UMMA_DUMP") : nullptr;
+  if (dump_path) {  // bring-up aid: raw accumulator of unit 0 -> file
+    if ((rc = ix->debug.ensure(kBlockRows * kBlockRows * sizeof(float))) != LK_OK) return rc;
+    LK_CUDA(cudaMemsetAsync(ix->debug.p, 0xFF, kBlockRows * kBlockRows * sizeof(float), st));
+    a.debug_tile = ix->debug.as<float>();
+  }
   if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   if (rc != LK_OK) return rc;
@@ -448,6 +455,16 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   else rc = launch_search_simt(a, ix->sm_count, st);
   if (rc != LK_OK) return rc;
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[2], st));
+
+  if (dump_path) {
+    std::vector<float> tile(kBlockRows * kBlockRows);
+    LK_CUDA(cudaMemcpyAsync(tile.data(), ix->debug.p, tile.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaStreamSynchronize(st));
+    if (FILE* f = fopen(dump_path, "wb")) {
+      fwrite(tile.data(), sizeof(float), tile.size(), f);
+      fclose(f);
+    }
+  }
 
   // 4. merge the per-CTA lists
   float* d_s = out_scores;

@@ -96,6 +96,7 @@ struct SearchArgs {
   float* part_scores;      // [n_queries, n_lists, ksel]
   int32_t* part_idx;       // [n_queries, n_lists, ksel]
   int* err_flag;           // device int, set non-zero by a kernel that timed out
+  float* debug_tile;       // optional [128 x 128] dump of unit 0's raw accumulator (bring-up aid)
 };
 
 int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);

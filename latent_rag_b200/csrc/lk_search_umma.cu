@@ -28,6 +28,8 @@
 // The operand images in HBM are already in the tcgen05 canonical K-major no-swizzle
 // layout (lk_common.cuh), so the producer needs no tensor map: every copy is a
 // contiguous 16 KB UBLKCP.
+#include <cstdlib>
+
 #include "lk_ptx.cuh"
 #include "lk_topk.cuh"
 
@@ -69,6 +71,7 @@ struct UmmaParams {
   float* part_scores;    // [n_queries, n_lists, KSEL]
   int32_t* part_idx;
   int* err_flag;
+  float* debug_tile;     // [128 queries][128 rows] raw dot products of unit 0, or null
   uint32_t lbo, sbo;
 };
 
@@ -288,6 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
                                (uint32_t)(acc.idx * kBlockRows + ch * kColsPerWarp + chunk * 32);
         ptx::tmem_ld32(taddr, r);
         ptx::tmem_wait_ld();
+        if (p.debug_tile != nullptr && u == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            p.debug_tile[lane_q * kBlockRows + ch * kColsPerWarp + chunk * 32 + j] = __uint_as_float(r[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float dot = __uint_as_float(r[j]);
@@ -393,8 +401,11 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.part_scores = a.part_scores;
   p.part_idx = a.part_idx;
   p.err_flag = a.err_flag;
+  p.debug_tile = a.debug_tile;
   p.lbo = kLbo;
   p.sbo = kSbo;
+  if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
+  if (const char* e = getenv("LK_UMMA_SBO")) p.sbo = (uint32_t)atoi(e);
   const bool qres = q_resident(a.g);
   const int stage = qres ? kKBlockBytes : 2 * kKBlockBytes;
   const size_t smem = (size_t)kHeaderBytes + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +

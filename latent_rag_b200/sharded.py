@@ -115,11 +115,22 @@ class ShardedRetriever:
         return self.index.search(queries, k, idx_base=self.row_offset, device_out=True)
 
     def search(self, queries: torch.Tensor, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Global top-k as numpy (scores float32 [B,k'], ids int64 [B,k']), k' = min(k, N_total)."""
+        t0 = time.perf_counter()
+        out_d, out_i = self.search_tensors(queries, k)
+        if torch.is_tensor(out_d):
+            out_d, out_i = out_d.cpu().numpy(), out_i.cpu().numpy()
+        b = 1 if queries.dim() == 1 else queries.size(0)
+        self._stats.add_search_batch(batch_size=b, seconds=time.perf_counter() - t0)
+        return np.asarray(out_d, dtype=np.float32), np.asarray(out_i, dtype=np.int64)
+
+    def search_tensors(self, queries: torch.Tensor, k: int):
+        """Same as `search` but leaves the result where the merge produced it (CUDA tensors on
+        the native path: no host synchronisation)."""
         if queries.dim() == 1:
             queries = queries.unsqueeze(0)
         b = queries.size(0)
         k = min(int(k), self.n_total)
-        t0 = time.perf_counter()
         # 1. local top-k with global ids, padded to k when the shard is smaller than k
         d = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.comm_device)
         i = torch.full((b, k), -1, dtype=torch.int64, device=self.comm_device)
@@ -145,10 +156,7 @@ class ShardedRetriever:
             from .engine import merge_topk
 
             out_d, out_i = merge_topk(cd, ci, k)
-        if torch.is_tensor(out_d):
-            out_d, out_i = out_d.cpu().numpy(), out_i.cpu().numpy()
-        self._stats.add_search_batch(batch_size=b, seconds=time.perf_counter() - t0)
-        return np.asarray(out_d, dtype=np.float32), np.asarray(out_i, dtype=np.int64)
+        return out_d, out_i
 
     def retrieve(self, query_emb: torch.Tensor, top_k: int = 10):
         d, i = self.search(query_emb, top_k)

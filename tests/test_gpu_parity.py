@@ -1,0 +1,401 @@
+"""Parity of the CUDA path (through the retriever classes -> ctypes -> C ABI) with the CPU
+oracle and with the committed outputs of the reference.  Run on a B200: pytest -m gpu.
+
+Tolerance (BASELINE.json north_star): identical top-k indices except at score ties within
+1e-5 relative; scores within 1e-5 * max(1, |s|).  bf16 storage is compared with the
+reference/oracle fed the SAME bf16-rounded values.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.golden import inputs
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def lrb():
+    import latent_rag_b200 as m
+
+    m._native.require_device()
+    return m
+
+
+def _assert_topk(d_ref, i_ref, d, i, rtol=RTOL):
+    ok, why = oracle.topk_equivalent(d_ref, i_ref, d, i, rtol=rtol)
+    assert ok, why
+
+
+def _oracle(emb, q, k, metric):
+    return oracle.bruteforce_search(oracle.bruteforce_build(emb, metric), q, k, metric)
+
+
+def test_native_library_is_loaded(lrb):
+    lrb.ExactIndex(8, 8).close()
+    with open("/proc/self/maps") as f:
+        assert "liblatentknn.so" in f.read()
+    assert lrb._native.launch_count() >= 0
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's own test vectors (test/test_retrieval.py:61-83), exact fp32 path
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nq,dim", inputs.SMALL_CASES)
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_fp32_path_matches_reference_outputs(lrb, golden, n, nq, dim, metric):
+    g = golden("retrieval_small.npz")
+    emb = inputs.reference_test_embeddings(n, dim)
+    r = lrb.BruteForceRetriever(emb.clone(), [f"doc_{j}" for j in range(n)], list(range(n)), metric=metric,
+                                precision="fp32")
+    d, i = r.search(emb[:nq], 5)
+    assert d.dtype == np.float32 and i.dtype == np.int64 and d.shape == (nq, 5)
+    _assert_topk(g[f"{n}_{nq}_{dim}_{metric}_D"], g[f"{n}_{nq}_{dim}_{metric}_I"], d, i)
+    np.testing.assert_array_equal(i[:, 0], np.arange(nq))
+    texts, scores, ids = r.retrieve(emb[0], top_k=5)  # bruteforce.py:86-92
+    assert texts == [f"doc_{j}" for j in ids] and len(scores) == 5
+    if metric == "cosine":
+        assert ids == g[f"{n}_{nq}_{dim}_retrieve_ids"].tolist()
+        np.testing.assert_allclose(scores, g[f"{n}_{nq}_{dim}_retrieve_scores"], rtol=1e-5, atol=1e-6)
+    st = r.get_stats()
+    assert st["search_calls"] == 2 and len(st["per_query_ms"]) == 2 and st["build_time_s"] > 0
+
+
+@pytest.mark.parametrize("precision,kernel", [("fp32", "simt"), ("bf16", "simt"), ("bf16", "umma")])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_edge_cases(lrb, golden, precision, kernel, metric, monkeypatch):
+    """k > N clamps (bruteforce.py:81), 1-D query (:59-60), zero corpus row / zero query."""
+    monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
+    g = golden("retrieval_edge.npz")
+    emb, q = inputs.edge_case_inputs()  # exactly representable in bf16
+    r = lrb.BruteForceRetriever(emb, [""] * len(emb), None, metric=metric, precision=precision)
+    d, i = r.search(q, 50)
+    assert d.shape == (3, 7)
+    _assert_topk(g[f"clamp_{metric}_D"], g[f"clamp_{metric}_I"], d, i)
+    d1, i1 = r.search(q[1], 3)
+    assert d1.shape == (1, 3)
+    _assert_topk(g[f"oned_{metric}_D"], g[f"oned_{metric}_I"], d1, i1)
+    if metric == "cosine":
+        assert np.all(d[2] == 0.0)
+
+
+# ---------------------------------------------------------------------------------------
+# bf16 storage: both kernels against the reference run on the same bf16-rounded values
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["simt", "umma"])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_bf16_mid_case_matches_reference_outputs(lrb, golden, kernel, metric, monkeypatch):
+    monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
+    g = golden("retrieval_mid.npz")
+    emb, q = inputs.mid_case_inputs()
+    r = lrb.BruteForceRetriever(emb, [""] * len(emb), None, metric=metric)
+    d, i = r.search(q, 10)
+    _assert_topk(g[f"{metric}_D"], g[f"{metric}_I"], d, i)
+    # CUDA-resident inputs take the same path
+    d2, i2 = r.search(q.cuda(), 10)
+    np.testing.assert_array_equal(i, i2)
+    np.testing.assert_array_equal(d, d2)
+
+
+SHAPES = [
+    # n, b, dim, k
+    (1, 1, 64, 1),
+    (100, 10, 64, 5),
+    (127, 3, 32, 10),
+    (129, 130, 64, 10),
+    (1000, 50, 32, 5),
+    (5000, 257, 100, 7),
+    (20000, 300, 384, 10),
+    (20000, 77, 384, 32),
+    (3000, 40, 768, 10),
+    (3000, 200, 768, 30),
+    (40000, 1, 384, 10),
+    (2500, 1500, 64, 10),
+]
+
+
+@pytest.mark.parametrize("n,b,dim,k", SHAPES)
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
+    """tcgen05 kernel over ragged shapes: partial row blocks, partial query tiles, several
+    query tiles per CTA range, K padding (dim 32/100), streamed-Q (dim 768), k in both
+    register-list sizes."""
+    monkeypatch.setenv("LK_FORCE_KERNEL", "umma")
+    rng = np.random.default_rng(n * 7 + b)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    if n >= 8 and b >= 4:
+        q[::4] = oracle.bf16_round(emb[(np.arange(0, b, 4) * 13) % n] + 0.05 * q[::4])
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric)
+    d, i = r.search(q, k)
+    d_ref, i_ref = _oracle(emb, q, k, metric)
+    _assert_topk(d_ref, i_ref, d, i)
+
+
+@pytest.mark.parametrize("n,b,dim,k", [(1000, 50, 32, 5), (20000, 33, 384, 10), (3000, 9, 768, 100), (700, 5, 48, 128)])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_simt_kernel_matches_oracle(lrb, n, b, dim, k, precision, metric, monkeypatch):
+    monkeypatch.setenv("LK_FORCE_KERNEL", "simt")
+    rng = np.random.default_rng(n + b)
+    emb = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32))
+    if precision == "bf16":
+        emb, q = oracle.bf16_round(emb), oracle.bf16_round(q)
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric, precision=precision)
+    d, i = r.search(q, k)
+    d_ref, i_ref = _oracle(emb, q, k, metric)
+    _assert_topk(d_ref, i_ref, d, i)
+
+
+@pytest.mark.parametrize("kernel", ["simt", "umma"])
+def test_ties_resolve_to_the_lowest_index(lrb, kernel, monkeypatch):
+    """Duplicate rows give exactly equal scores; the engine's order is (score desc, index asc)
+    whatever the partitioning.  (torch.topk's tie order is unspecified.)"""
+    monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
+    rng = np.random.default_rng(2)
+    base = oracle.bf16_round(torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32)))
+    emb = torch.cat([base, base, base])  # rows j, j+300, j+600 identical
+    r = lrb.BruteForceRetriever(emb, [""] * 900, None, metric="euclidean")
+    d, i = r.search(base[:20], 6)
+    for row in range(20):
+        assert i[row, :3].tolist() == [row, row + 300, row + 600]
+        assert d[row, 0] == d[row, 1] == d[row, 2]
+    d_ref, i_ref = _oracle(emb, base[:20], 6, "euclidean")
+    _assert_topk(d_ref, i_ref, d, i)
+
+
+def test_metrics_identical_to_oracle_results(lrb):
+    """north_star: identical Recall@k, MRR and nDCG."""
+    emb, q = inputs.mid_case_inputs()
+    r = lrb.BruteForceRetriever(emb, [""] * len(emb), None, metric="cosine")
+    _, i = r.search(q, 10)
+    _, i_ref = _oracle(emb, q, 10, "cosine")
+    rng = np.random.default_rng(0)
+    relevant = [[int(i_ref[j, rng.integers(0, 10)]), int(rng.integers(0, len(emb)))] for j in range(len(q))]
+    names = ["Recall@10", "MRR@10", "nDCG@10"]
+    got = oracle.evaluate_retrieval([row.tolist() for row in i], relevant, names)
+    ref = oracle.evaluate_retrieval([row.tolist() for row in i_ref], relevant, names)
+    assert got == ref
+
+
+# ---------------------------------------------------------------------------------------
+# FAISSEmbeddingRetriever (flatip) mirror: the reference's own tests
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nq,dim", inputs.SMALL_CASES)
+def test_faiss_matches_bruteforce(lrb, n, nq, dim):
+    """test/test_retrieval.py:61-83: ordered doc_ids of FlatIP == brute force, k=5."""
+    emb = inputs.reference_test_embeddings(n, dim)
+    texts = [f"doc_{j}" for j in range(n)]
+    ids = list(range(n))
+    bf = lrb.BruteForceRetriever(emb.clone(), texts, ids, metric="cosine")
+    fr = lrb.FAISSEmbeddingRetriever(embedding_dim=dim, index_type="flatip", use_gpu=False)
+    fr.build(emb.clone(), texts, ids, train=False)
+    for qv in emb[:nq]:
+        docs_f, _, ids_f = fr.retrieve(qv, top_k=5)
+        docs_b, _, ids_b = bf.retrieve(qv, top_k=5)
+        assert ids_f == ids_b
+        assert docs_f == [texts[j] for j in ids_f] and docs_b == [texts[j] for j in ids_b]
+
+
+def test_faiss_index_persistence(lrb, tmp_path):
+    """test/test_retrieval.py:86-119."""
+    emb = inputs.reference_test_embeddings(200, 48)
+    texts = [f"chunk_{j}" for j in range(200)]
+    ids = list(range(200))
+    path = tmp_path / "test.faiss"
+    r1 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    r1.build(emb, texts, ids, train=False)
+    r2 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    docs1, scores1, ids1 = r1.retrieve(emb[0], top_k=10)
+    docs2, scores2, ids2 = r2.retrieve(emb[0], top_k=10)
+    assert ids1 == ids2 and docs1 == docs2
+    np.testing.assert_allclose(scores1, scores2, rtol=1e-6)
+    # an incompatible fingerprint rebuilds from scratch (FAISSEmbeddingRetriever.py:225-250)
+    r2.build(emb[:50], texts[:50], ids[:50], ae_type="vae")
+    assert r2.index.size == 50 and len(r2._texts) == 50
+
+
+def test_faiss_semantics(lrb):
+    emb = inputs.reference_test_embeddings(3, 16)
+    fr = lrb.FAISSEmbeddingRetriever(16, index_type="flatip")
+    fr.build(emb, ["a", "b", "c"])  # default doc id -1 (FAISSEmbeddingRetriever.py:296)
+    assert fr._doc_ids == [-1, -1, -1]
+    d, i = fr.search(emb[:2], 5)  # [upstream] pads instead of clamping
+    assert i.shape == (2, 5) and (i[:, 3:] == -1).all() and (d[:, 3:] == -np.finfo(np.float32).max).all()
+    fr.build(emb, ["d", "e", "f"])  # every build appends (FAISSEmbeddingRetriever.py:252-257,294-296)
+    assert fr.index.size == 6 and fr._texts == ["a", "b", "c", "d", "e", "f"]
+    with pytest.raises(ValueError, match="Index type not supported"):
+        lrb.FAISSEmbeddingRetriever(16, index_type="lsh")
+    with pytest.raises(AssertionError):
+        fr.build(emb, ["x"])
+    r = lrb.build_retriever(emb, ["a", "b", "c"], [7, 8, 9], {"backend": "faiss", "index_type": "flatip"})
+    assert r.retrieve(emb[1], top_k=1)[2] == [8]
+    r = lrb.build_retriever(emb, ["a", "b", "c"], [7, 8, 9], {"backend": "bruteforce"})
+    assert isinstance(r, lrb.BruteForceRetriever) and r.retrieve(emb[2], top_k=1)[2] == [9]
+
+
+# ---------------------------------------------------------------------------------------
+# Mahalanobis (our definition; the reference has none)
+# ---------------------------------------------------------------------------------------
+def _aniso(n, d, seed):
+    rng = np.random.default_rng(seed)
+    a = np.diag(np.linspace(0.2, 2.0, d)) @ np.linalg.qr(rng.standard_normal((d, d)))[0]
+    return torch.from_numpy((rng.standard_normal((n, d)) @ a).astype(np.float32))
+
+
+@pytest.mark.parametrize("kernel", ["simt", "umma"])
+def test_mahalanobis_bf16_matches_whitened_oracle(lrb, kernel, monkeypatch):
+    """The engine whitens in fp64, rounds to bf16 and runs the L2 path; the oracle does the
+    same on the CPU (fp64 whitening -> fp32 -> bf16 -> reference euclidean search)."""
+    monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
+    emb, q = _aniso(3000, 64, 1), _aniso(40, 64, 2)
+    p = oracle.mahalanobis_precision(emb)
+    r = lrb.BruteForceRetriever(emb, [""] * 3000, None, metric="mahalanobis", precision_matrix=p)
+    d, i = r.search(q, 10)
+    lw = oracle.mahalanobis_whitener(p)
+    ew = oracle.bf16_round(torch.from_numpy((emb.numpy().astype(np.float64) @ lw).astype(np.float32)))
+    qw = oracle.bf16_round(torch.from_numpy((q.numpy().astype(np.float64) @ lw).astype(np.float32)))
+    d_ref, i_ref = _oracle(ew, qw, 10, "euclidean")
+    _assert_topk(d_ref, i_ref, d, i)
+
+
+def test_mahalanobis_fp32_matches_fp64_definition(lrb):
+    emb, q = _aniso(2000, 48, 3), _aniso(25, 48, 4)
+    r = lrb.BruteForceRetriever(emb, [""] * 2000, None, metric="mahalanobis", precision="fp32")
+    d, i = r.search(q, 10)
+    d_ref, i_ref = oracle.mahalanobis_search(emb, q, 10)  # fp64, precision estimated from the corpus
+    _assert_topk(d_ref, i_ref, d, i, rtol=2e-4)  # fp32 storage of whitened vectors vs fp64
+
+
+# ---------------------------------------------------------------------------------------
+# autoencoder encoders against the shipped checkpoints' reference outputs
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["vae", "dae", "cae"])
+def test_ae_encoder_matches_reference_outputs(lrb, golden, kind):
+    ae = lrb.load_autoencoder(kind, os.path.join(os.path.dirname(__file__), "golden", f"ae_weights_{kind}.npz"))
+    x = inputs.ae_input()
+    z = ae.encode(x)
+    if isinstance(z, tuple):  # retrieval/embedder.py:44-45
+        z = z[0]
+    assert z.shape == (48, 64) and z.dtype == torch.float32 and not z.is_cuda
+    np.testing.assert_allclose(z.numpy(), golden("ae_golden.npz")[f"{kind}_z"], rtol=1e-4, atol=2e-6)
+    zc = ae.encode(x.cuda())
+    zc = zc[0] if isinstance(zc, tuple) else zc
+    assert zc.is_cuda
+    np.testing.assert_array_equal(zc.cpu().numpy(), z.numpy())
+    if kind == "cae":  # test/test_models.py:26-36
+        assert torch.allclose(z.norm(dim=-1), torch.ones(48), atol=1e-6)
+
+
+def test_ae_encoder_ragged_batch_and_small_dims(lrb):
+    rng = np.random.default_rng(4)
+    sd = {"encoder.0.weight": rng.standard_normal((8, 16)).astype(np.float32),
+          "encoder.0.bias": rng.standard_normal(8).astype(np.float32),
+          "encoder.2.weight": rng.standard_normal((4, 8)).astype(np.float32),
+          "encoder.2.bias": rng.standard_normal(4).astype(np.float32)}
+    for kind, cls in (("dae", lrb.DenoisingAutoencoder), ("cae", lrb.ContrastiveAutoencoder)):
+        ae = cls(16, 4, 8)  # the shapes of test/test_models.py
+        ae.load_state_dict(sd)
+        x = torch.from_numpy(rng.standard_normal((77, 16)).astype(np.float32))
+        z = ae.encode(x)
+        ref = oracle.ae_encode(x, oracle.load_encoder_weights(sd, kind), kind)
+        np.testing.assert_allclose(z.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_latent_pipeline_config2_shape(lrb):
+    """config 2 in miniature: encode corpus + queries with the shipped CAE, cosine top-10."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    ae = lrb.load_autoencoder("cae", os.path.join(gold, "ae_weights_cae.npz"))
+    rng = np.random.default_rng(6)
+    docs = torch.from_numpy(rng.standard_normal((6000, 384)).astype(np.float32))
+    docs /= docs.norm(dim=1, keepdim=True)
+    qs = docs[:64] + 0.05 * torch.from_numpy(rng.standard_normal((64, 384)).astype(np.float32))
+    zd, zq = ae.encode(docs.cuda()), ae.encode(qs.cuda())
+    r = lrb.BruteForceRetriever(zd, [""] * 6000, None, metric="cosine")
+    d, i = r.search(zq, 10)
+    w = oracle.load_encoder_weights(np.load(os.path.join(gold, "ae_weights_cae.npz")), "cae")
+    zd_ref = oracle.bf16_round(zd.cpu())  # the engine's own latents, rounded as it stores them
+    d_ref, i_ref = _oracle(zd_ref, oracle.bf16_round(zq.cpu()), 10, "cosine")
+    _assert_topk(d_ref, i_ref, d, i)
+    np.testing.assert_allclose(zd.cpu().numpy(), oracle.ae_encode(docs, w, "cae").numpy(), rtol=1e-4, atol=2e-6)
+    assert (i[:, 0] == np.arange(64)).mean() > 0.9
+
+
+# ---------------------------------------------------------------------------------------
+# merge kernel + sharding
+# ---------------------------------------------------------------------------------------
+def test_merge_kernel_matches_oracle(lrb):
+    rng = np.random.default_rng(12)
+    for b, lists, ln, k in [(1, 8, 10, 10), (33, 3, 100, 100), (257, 8, 10, 7), (5, 2, 128, 128)]:
+        cd = rng.standard_normal((b, lists, ln)).astype(np.float32)
+        ci = rng.permutation(b * lists * ln).reshape(b, lists, ln).astype(np.int64)
+        ci[:, -1, -2:] = -1  # padding
+        cd[0, 0, :2] = cd[0, 1, 0]  # ties
+        d, i = lrb.merge_topk(cd, ci, k)
+        d_ref, i_ref = oracle.merge_topk(cd, ci, k)
+        np.testing.assert_array_equal(i, i_ref)
+        np.testing.assert_array_equal(d, d_ref)
+        dg, ig = lrb.merge_topk(torch.from_numpy(cd).cuda(), torch.from_numpy(ci).cuda(), k)
+        np.testing.assert_array_equal(ig.cpu().numpy(), i_ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_row_sharding_is_invisible(lrb, world):
+    """Searching `world` row shards (global ids via idx_base) and merging equals the unsharded
+    search bit for bit -- the multi-GPU data path run on one GPU."""
+    rng = np.random.default_rng(31)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((5003, 384)).astype(np.float32)))
+    q = oracle.bf16_round(torch.from_numpy(rng.standard_normal((70, 384)).astype(np.float32)))
+    whole = lrb.BruteForceRetriever(emb, [""] * 5003, None, metric="euclidean")
+    d0, i0 = whole.search(q, 10)
+    cd, ci = [], []
+    for lo, hi in lrb.shard_bounds(5003, world):
+        ix = lrb.ExactIndex(384, hi - lo, metric="euclidean")
+        ix.add(emb[lo:hi])
+        d, i = ix.search(q, 10, idx_base=lo, device_out=True)
+        cd.append(d)
+        ci.append(i)
+    d, i = lrb.merge_topk(torch.stack(cd, 1), torch.stack(ci, 1), 10)
+    np.testing.assert_array_equal(i.cpu().numpy(), i0)
+    np.testing.assert_array_equal(d.cpu().numpy(), d0)
+    sr = lrb.ShardedRetriever(emb, 0, "euclidean")  # world 1, native merge
+    ds, is_ = sr.search(q, 10)
+    np.testing.assert_array_equal(is_, i0)
+
+
+# ---------------------------------------------------------------------------------------
+# full-size properties (no oracle at this scale)
+# ---------------------------------------------------------------------------------------
+def test_large_corpus_properties(lrb):
+    """2M x 384 bf16 generated on the device: planted neighbours are found, scores sorted,
+    indices unique and in range, both kernels agree, batch-1 equals its row of the batch."""
+    n, dim, b = 2_000_000, 384, 256
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    ix = lrb.ExactIndex(dim, n, metric="cosine")
+    planted = {}
+    for lo in range(0, n, 250_000):
+        chunk = torch.randn((250_000, dim), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+        for j in range(lo, lo + 250_000, 31_250):
+            planted[j] = chunk[j - lo].float().cpu()
+        ix.add(chunk)
+    assert ix.size == n
+    rows = sorted(planted)[:b // 4]
+    q = torch.randn((b, dim), generator=torch.Generator().manual_seed(4321))
+    for t, row in enumerate(rows):
+        q[t] = planted[row] + 0.1 * q[t]
+    q = oracle.bf16_round(q)
+    d, i = ix.search(q, 10)
+    assert (i[: len(rows), 0] == np.asarray(rows)).all()
+    assert (np.diff(d, axis=1) <= 0).all() and (i >= 0).all() and (i < n).all()
+    assert all(len(set(row.tolist())) == 10 for row in i)
+    d1, i1 = ix.search(q[3], 10)
+    np.testing.assert_array_equal(i1[0], i[3])
+    np.testing.assert_array_equal(d1[0], d[3])
+    ds, is_ = ix.search(q[:8], 10, kernel="simt")
+    _assert_topk(ds, is_, d[:8], i[:8])
