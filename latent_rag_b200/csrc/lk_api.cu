@@ -78,8 +78,8 @@ TileGeom make_geom(int dim, int storage) {
   TileGeom g;
   g.dim = dim;
   g.elem_bytes = storage == LK_BF16 ? 2 : 4;
-  g.dim_pad = round_up(dim, storage == LK_BF16 ? kKBlockElems : 4);
-  g.chunks = g.dim_pad * g.elem_bytes / kChunkBytes;
+  g.dim_pad = round_up(dim, kRowBytes / g.elem_bytes);
+  g.kblocks = g.dim_pad * g.elem_bytes / kRowBytes;
   return g;
 }
 

@@ -13,21 +13,29 @@ namespace lk {
 // ---------------------------------------------------------------------------------
 // Data layout in HBM (DESIGN.md "Data layout")
 //
-// The corpus is stored as ROW BLOCKS of 128 rows.  Inside a block the bytes are the
-// tcgen05 "K-major, no-swizzle" canonical operand image:
+// The corpus is stored as ROW BLOCKS of 128 rows, each split into K BLOCKS of 128 bytes
+// per row (64 bf16 or 32 fp32).  One (row block, K block) SLAB is 128 rows x 128 B = 16 KB
+// and is byte for byte the tcgen05 "K-major, SWIZZLE_128B" shared-memory operand image:
 //
-//     block[kc][r][16 bytes]      kc = 16-byte K chunk (8 bf16 or 4 fp32), r = 0..127
+//     slab[r][p][16 bytes]   r = 0..127, p = physical 16-byte chunk = c ^ (r & 7)
+//                            c = logical chunk 0..7 (8 bf16 / 4 fp32 each)
 //
-// so that (a) one 16 KB cp.async.bulk brings a [128 rows x 64 K] bf16 operand slab into
-// shared memory ready for tcgen05.mma (core matrix = 8 rows x 16 B contiguous,
-// SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks), and (b) a SIMT warp
-// reading "its" rows for one kc touches 512 contiguous bytes.
+// i.e. rows are 128 B apart, 8-row groups 1024 B apart (SBO), and the 16-byte chunks of a
+// row are XOR-swizzled with the row index so that tcgen05.mma reads operands at full
+// shared-memory bandwidth.  A 16 KB cp.async.bulk brings a slab into a 1024-aligned stage
+// with no tensor map.  Slabs are ordered [row block][K block].
 // ---------------------------------------------------------------------------------
 constexpr int kBlockRows = 128;       // rows per row block (= UMMA M / N granule)
 constexpr int kChunkBytes = 16;       // one K chunk of one row
-constexpr int kKBlockElems = 64;      // bf16 elements per pipeline K block
+constexpr int kRowBytes = 128;        // bytes of one row inside a K block (swizzle span)
+constexpr int kSlabBytes = kBlockRows * kRowBytes;  // 16384
 constexpr int kMaxK = 128;            // largest supported top-k
 constexpr int kSimtQG = 4;            // queries per CTA pass in the SIMT kernel
+
+// byte offset of logical chunk c (0..7) of row r inside a slab
+__host__ __device__ inline int slab_chunk_offset(int r, int c) {
+  return r * kRowBytes + ((c ^ (r & 7)) << 4);
+}
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -64,10 +72,11 @@ void count_launch(int n = 1);
 // ---------------------------------------------------------------------------------
 struct TileGeom {
   int dim;          // logical dimension
-  int dim_pad;      // padded to a multiple of 64 elements (bf16) / 64 (fp32)
+  int dim_pad;      // padded to whole K blocks: a multiple of 64 (bf16) / 32 (fp32) elements
   int elem_bytes;   // 2 (bf16) or 4 (fp32)
-  int chunks;       // dim_pad * elem_bytes / 16
-  __host__ __device__ int64_t block_bytes() const { return (int64_t)chunks * kBlockRows * kChunkBytes; }
+  int kblocks;      // dim_pad * elem_bytes / 128
+  __host__ __device__ int chunks() const { return kblocks * 8; }
+  __host__ __device__ int64_t block_bytes() const { return (int64_t)kblocks * kSlabBytes; }
 };
 
 // rows [n, dim] (fp32 or bf16 row-major, device) -> tiled storage starting at row

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(const InT* __restrict__ 
 
   // pass 2: scatter the row into its block, one 16-byte chunk per lane per step
   const int64_t g = row0 + r;
-  unsigned char* blk = tiles + (g / kBlockRows) * block_bytes + (g % kBlockRows) * kChunkBytes;
+  const int rin = (int)(g % kBlockRows);
+  unsigned char* blk = tiles + (g / kBlockRows) * block_bytes;
   for (int kc = lane; kc < chunks; kc += 32) {
     alignas(16) OutT v[E];
 #pragma unroll
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(const InT* __restrict__ 
         reinterpret_cast<float*>(v)[e] = x;
       }
     }
-    *reinterpret_cast<uint4*>(blk + (int64_t)kc * (kBlockRows * kChunkBytes)) =
+    // K block kc>>3, logical chunk kc&7 -> swizzled position inside the slab
+    *reinterpret_cast<uint4*>(blk + (int64_t)(kc >> 3) * kSlabBytes + slab_chunk_offset(rin, kc & 7)) =
         *reinterpret_cast<const uint4*>(v);
   }
   if (lane == 0) {
@@ -106,7 +108,7 @@ int launch_tile_rows(const void* rows, int rows_dtype, int64_t n, const TileGeom
   unsigned char* t = static_cast<unsigned char*>(tiles);
 #define LK_TILE(IN, OUT)                                                                      \
   tile_rows_kernel<IN, OUT><<<grid, warps * 32, 0, st>>>(static_cast<const IN*>(rows), n, g.dim, \
-                                                         g.chunks, g.block_bytes(), t, side,   \
+                                                         g.chunks(), g.block_bytes(), t, side,   \
                                                          row0, side_mode, prenorm)
   if (g.elem_bytes == 2) {
     if (rows_dtype == LK_F32) LK_TILE(float, __nv_bfloat16);

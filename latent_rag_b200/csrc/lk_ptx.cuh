@@ -115,12 +115,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---- descriptors ----------------------------------------------------------------------
-// Shared-memory matrix descriptor, K-major, no swizzle (layout_type 0), sm_100 version 1:
-//   [0,14) start>>4   [16,30) LBO>>4 (between K chunks)   [32,46) SBO>>4 (between 8-row
-//   groups)   [46,48) version=1   [61,64) layout type
-__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (sm_100 format), K-major operand in the SWIZZLE_128B
+// layout: rows of 128 bytes, 8-row groups `sbo_bytes` apart, 16-byte chunks XOR-swizzled
+// by (row & 7); the slab base must be 1024-byte aligned and a K step of 16 elements is a
+// +32-byte advance of the start address.
+//   [0,14) start>>4   [16,30) LBO>>4 (ignored for swizzled K-major)   [32,46) SBO>>4
+//   [46,48) version=1   [61,64) layout type (0 none, 2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = 2u) {
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 // Instruction descriptor for kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10), both
 // K-major, N>>3 at [17,23), M>>4 at [24,29)

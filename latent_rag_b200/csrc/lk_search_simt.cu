@@ -30,9 +30,11 @@ template <> struct Chunk<__nv_bfloat16> {
   }
 };
 
+// the 8 chunks of a row's 128-byte line are fetched by 8 consecutive requests of the same
+// thread, so let the line live in L1 between them
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
@@ -65,9 +67,9 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
     const int64_t q = q0 + g;
     float v = 0.f;
     if (q < a.n_queries) {
-      const unsigned char* p = qt + (q / kBlockRows) * block_bytes +
-                               (int64_t)(c / E) * (kBlockRows * kChunkBytes) +
-                               (q % kBlockRows) * kChunkBytes + (c % E) * sizeof(ElemT);
+      const int gc = c / E;  // global 16-byte chunk of the row
+      const unsigned char* p = qt + (q / kBlockRows) * block_bytes + (int64_t)(gc >> 3) * kSlabBytes +
+                               slab_chunk_offset((int)(q % kBlockRows), gc & 7) + (c % E) * sizeof(ElemT);
       if (sizeof(ElemT) == 2) v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
       else v = *reinterpret_cast<const float*>(p);
     }
@@ -80,37 +82,29 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
   __syncthreads();
 
   const unsigned char* tiles = static_cast<const unsigned char*>(a.tiles);
-  const int chunks = a.g.chunks;
+  const int kblocks = a.g.kblocks;
+  const int sw = t & 7;  // this row's chunk swizzle
   for (int64_t blk = blk_lo; blk < blk_hi; ++blk) {
-    const uint4* src = reinterpret_cast<const uint4*>(tiles + blk * block_bytes) + t;
+    const unsigned char* row = tiles + blk * block_bytes + t * kRowBytes;
     float acc[QG];
 #pragma unroll
     for (int g = 0; g < QG; ++g) acc[g] = 0.f;
-    int kc = 0;
-    for (; kc + 4 <= chunks; kc += 4) {  // 4 independent 16-byte loads in flight per thread
-      uint4 u[4];
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const uint4* src = reinterpret_cast<const uint4*>(row + (int64_t)kb * kSlabBytes);
+      uint4 u[8];  // the row's whole 128-byte line of this K block: 8 independent loads;
+                   // logical chunk c sits at physical position c ^ (row & 7)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) u[j] = ld_stream(src + (int64_t)(kc + j) * kBlockRows);
+      for (int c = 0; c < 8; ++c) u[c] = ld_stream(src + (c ^ sw));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int c = 0; c < 8; ++c) {
         float x[E];
-        Chunk<ElemT>::unpack(u[j], x);
+        Chunk<ElemT>::unpack(u[c], x);
 #pragma unroll
         for (int g = 0; g < QG; ++g) {
-          const float* qg = qs + g * dim_pad + (kc + j) * E;
+          const float* qg = qs + g * dim_pad + (kb * 8 + c) * E;
 #pragma unroll
           for (int e = 0; e < E; ++e) acc[g] = fmaf(x[e], qg[e], acc[g]);
         }
-      }
-    }
-    for (; kc < chunks; ++kc) {
-      float x[E];
-      Chunk<ElemT>::unpack(ld_stream(src + (int64_t)kc * kBlockRows), x);
-#pragma unroll
-      for (int g = 0; g < QG; ++g) {
-        const float* qg = qs + g * dim_pad + kc * E;
-#pragma unroll
-        for (int e = 0; e < E; ++e) acc[g] = fmaf(x[e], qg[e], acc[g]);
       }
     }
     // epilogue of the reference formulas; rows past the end carry side = NaN -> NaN score

@@ -25,9 +25,9 @@
 //               columns, apply the metric (cosine norm / L2 expansion) with the per-row
 //               side value, compare against the k-th best, insert on the rare hit.
 //
-// The operand images in HBM are already in the tcgen05 canonical K-major no-swizzle
-// layout (lk_common.cuh), so the producer needs no tensor map: every copy is a
-// contiguous 16 KB UBLKCP.
+// The operand slabs in HBM are already the tcgen05 K-major SWIZZLE_128B shared-memory
+// image (lk_common.cuh), so the producer needs no tensor map: every copy is a contiguous
+// 16 KB UBLKCP into a 1024-aligned stage.
 #include <cstdlib>
 
 #include "lk_ptx.cuh"
@@ -44,12 +44,15 @@ constexpr int kColSplit = kEpiWarps / 4;                 // epilogue warps per l
 constexpr int kColsPerWarp = kBlockRows / kColSplit;     // 64 columns of each accumulator
 constexpr int kAccStages = 4;                            // 4 x 128 columns = all of TMEM
 constexpr int kTmemCols = kAccStages * kBlockRows;       // 512
-constexpr int kKBlockBytes = kBlockRows * kKBlockElems * 2;  // 16384
+constexpr int kKBlockElems = kRowBytes / 2;              // 64 bf16 per row per K block
+constexpr int kKBlockBytes = kSlabBytes;                 // 16384
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHeaderBytes = 256 + kEpiWarps * 2 * kColsPerWarp * 4;  // barriers + side rings
-constexpr uint32_t kLbo = kBlockRows * kChunkBytes;      // 2048: next K chunk
-constexpr uint32_t kSbo = 8 * kChunkBytes;               // 128 : next 8-row group
+constexpr int kAlignSlack = 1024;                        // stages must be 1024-aligned (swizzle atom)
+constexpr uint32_t kLbo = 16;                            // unused by swizzled K-major layouts
+constexpr uint32_t kSbo = 8 * kRowBytes;                 // 1024: next 8-row group
+constexpr uint32_t kUmmaKBytes = 32;                     // 16 bf16 = one MMA's K extent inside a row
 
 enum UmmaErr {
   kErrProdEmpty = 101, kErrProdQEmpty = 102, kErrMmaFull = 103, kErrMmaTmemEmpty = 104,
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   volatile int* abort_s = reinterpret_cast<volatile int*>(smem + 244);
   float* side_ring = reinterpret_cast<float*>(smem + 256);
   unsigned char* q_sm = smem + kHeaderBytes;
+  q_sm += (1024u - (ptx::smem_u32(q_sm) & 1023u)) & 1023u;  // swizzle atoms are 1024-byte aligned
   unsigned char* stage_sm = q_sm + (QRES ? p.nkb * kKBlockBytes : 0);
   constexpr int kStageBytes = QRES ? kKBlockBytes : 2 * kKBlockBytes;
 
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           const uint32_t q_addr = QRES ? ptx::smem_u32(q_sm + kb * kKBlockBytes) : e_addr + kKBlockBytes;
 #pragma unroll
           for (int k = 0; k < kKBlockElems / 16; ++k) {
-            const uint32_t off = (uint32_t)k * 2u * kLbo;  // 16 K elements = 2 chunks
+            const uint32_t off = (uint32_t)k * kUmmaKBytes;  // advance inside the 128-byte swizzled row
             ptx::umma_bf16(d_tmem, ptx::smem_desc(q_addr + off, p.lbo, p.sbo),
                            ptx::smem_desc(e_addr + off, p.lbo, p.sbo), idesc, (kb | k) != 0 ? 1u : 0u);
           }
@@ -347,12 +351,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   }
 }
 
-inline int n_kblocks(const TileGeom& g) { return g.dim_pad / kKBlockElems; }
+inline int n_kblocks(const TileGeom& g) { return g.kblocks; }
 inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
 inline int n_stages_for(const TileGeom& g) {
   const int stage = q_resident(g) ? kKBlockBytes : 2 * kKBlockBytes;
   const int q_bytes = q_resident(g) ? n_kblocks(g) * kKBlockBytes : 0;
-  int s = (kSmemBudget - kHeaderBytes - q_bytes) / stage;
+  int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage;
   return s > kMaxStages ? kMaxStages : s;
 }
 inline int ksel_for(int k) { return k <= 10 ? 10 : 32; }
@@ -360,7 +364,7 @@ inline int ksel_for(int k) { return k <= 10 ? 10 : 32; }
 }  // namespace
 
 int umma_supported(const TileGeom& g, int k) {
-  return g.elem_bytes == 2 && g.dim_pad % kKBlockElems == 0 && k >= 1 && k <= 32 && n_stages_for(g) >= 2;
+  return g.elem_bytes == 2 && g.kblocks >= 1 && k >= 1 && k <= 32 && n_stages_for(g) >= 2;
 }
 
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
@@ -408,7 +412,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   if (const char* e = getenv("LK_UMMA_SBO")) p.sbo = (uint32_t)atoi(e);
   const bool qres = q_resident(a.g);
   const int stage = qres ? kKBlockBytes : 2 * kKBlockBytes;
-  const size_t smem = (size_t)kHeaderBytes + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
+  const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
                       (size_t)p.n_stages * stage;
   const int64_t grid = p.total_units < sm_count ? p.total_units : sm_count;
   const int ksel = ksel_for(a.k);

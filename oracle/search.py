@@ -171,16 +171,30 @@ def merge_topk(cand_d: np.ndarray, cand_i: np.ndarray, k: int) -> Tuple[np.ndarr
 # ----------------------------------------------------------------------------
 # Tie-aware comparison (SURVEY.md section 8c "parity protocol")
 # ----------------------------------------------------------------------------
-def topk_equivalent(d_ref, i_ref, d_got, i_got, rtol: float = 1e-5) -> Tuple[bool, str]:
+def euclidean_scale(emb: torch.Tensor, queries: torch.Tensor) -> np.ndarray:
+    """Per-query magnitude of the terms the euclidean score cancels: |q|^2 + max|e|^2.
+    `-(q2 + e2 - 2qe)` is a difference of numbers of this size, so fp32 results (the
+    reference's included: it returns 1.5e-5 for an exact self-match at d=64) carry an
+    absolute error of a few ulp of THIS magnitude, not of the score."""
+    if queries.dim() == 1:
+        queries = queries.unsqueeze(0)
+    e2 = (emb.double() ** 2).sum(1).max().item() if emb.numel() else 0.0
+    return ((queries.double() ** 2).sum(1) + e2).numpy()
+
+
+def topk_equivalent(d_ref, i_ref, d_got, i_got, rtol: float = 1e-5, scale=None) -> Tuple[bool, str]:
     """True when `got` is the same top-k as `ref` up to score ties: rows must match
     index for index, except inside groups whose reference scores agree within
-    `rtol * max(1, |s|)`, where only the index *sets* (and the scores) must agree.
+    `rtol * max(1, |s|, scale)`, where only the index *sets* (and the scores) must
+    agree.  `scale` (per query) is the magnitude of the operands when the score is a
+    cancelling difference (see `euclidean_scale`); None for cosine.
     torch.topk's tie order is unspecified, so tie order is never asserted."""
     d_ref = np.asarray(d_ref); i_ref = np.asarray(i_ref)
     d_got = np.asarray(d_got); i_got = np.asarray(i_got)
     if d_ref.shape != d_got.shape or i_ref.shape != i_got.shape:
         return False, f"shape mismatch {d_ref.shape}/{i_ref.shape} vs {d_got.shape}/{i_got.shape}"
-    tol = rtol * np.maximum(1.0, np.abs(d_ref))
+    floor = np.ones((d_ref.shape[0], 1)) if scale is None else np.maximum(1.0, np.asarray(scale, dtype=np.float64).reshape(-1, 1))
+    tol = rtol * np.maximum(floor, np.abs(d_ref))
     bad = np.abs(d_ref - d_got) > tol
     if bad.any():
         r, c = np.argwhere(bad)[0]
@@ -191,7 +205,7 @@ def topk_equivalent(d_ref, i_ref, d_got, i_got, rtol: float = 1e-5) -> Tuple[boo
         c = 0
         while c < kk:
             e = c + 1
-            while e < kk and abs(d_ref[r, e] - d_ref[r, e - 1]) <= rtol * max(1.0, abs(d_ref[r, e])):
+            while e < kk and abs(d_ref[r, e] - d_ref[r, e - 1]) <= tol[r, e]:
                 e += 1
             ref_set, got_set = set(i_ref[r, c:e].tolist()), set(i_got[r, c:e].tolist())
             if ref_set != got_set:
@@ -199,7 +213,7 @@ def topk_equivalent(d_ref, i_ref, d_got, i_got, rtol: float = 1e-5) -> Tuple[boo
                 # members: accept when every differing index scores within tol of the cut
                 if e == kk:
                     ok = all(
-                        abs(d_got[r, c + j] - d_ref[r, kk - 1]) <= rtol * max(1.0, abs(d_ref[r, kk - 1]))
+                        abs(d_got[r, c + j] - d_ref[r, kk - 1]) <= tol[r, kk - 1]
                         for j, ix in enumerate(i_got[r, c:e].tolist())
                         if ix not in ref_set
                     )
