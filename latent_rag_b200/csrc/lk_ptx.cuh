@@ -114,6 +114,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+// one 32-bit column for the 32 lanes of this warp's quarter (column address is warp-uniform)
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+
 // ---- descriptors ----------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 format), K-major operand in the SWIZZLE_128B
 // layout: rows of 128 bytes, 8-row groups `sbo_bytes` apart, 16-byte chunks XOR-swizzled

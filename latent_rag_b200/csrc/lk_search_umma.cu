@@ -288,7 +288,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       ptx::tc_fence_after();
       const float* sd = my_side + slot * kColsPerWarp;
       const int32_t row0 = b * kBlockRows + ch * kColsPerWarp;
-#pragma unroll
+      // Fast path (branch-free, a few hundred instructions in total so it stays in the
+      // instruction cache): score every column and keep the running max.  Only when some
+      // lane's max beats its k-th best does the warp take the slow path, which holds the
+      // ONE copy of the insertion network and re-reads the candidate columns from TMEM.
+#pragma unroll 1
       for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
@@ -300,16 +304,30 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           for (int j = 0; j < 32; ++j)
             p.debug_tile[lane_q * kBlockRows + ch * kColsPerWarp + chunk * 32 + j] = __uint_as_float(r[j]);
         }
+        const float* sdc = sd + chunk * 32;
+        auto score = [&](float dot, float e_sd) -> float {
+          if (METRIC == LK_COSINE) return dot * e_sd;            // x 1/|e|; x 1/|q| at flush
+          return fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
+        };
+        float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float dot = __uint_as_float(r[j]);
-          const float e_sd = sd[chunk * 32 + j];
-          float s;
-          if (METRIC == LK_COSINE) s = dot * e_sd;                 // x 1/|e|; x 1/|q| at flush
-          else s = fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
-          if (s > thr) {                                           // NaN (padding rows) never passes
-            top.insert(s, row0 + chunk * 32 + j);
-            thr = top.threshold();
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, score(__uint_as_float(r[j]), sdc[j]));  // NaN never wins
+        if (__any_sync(0xffffffffu, m > thr)) {
+          unsigned pend = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            pend |= score(__uint_as_float(r[j]), sdc[j]) > thr ? (1u << j) : 0u;
+          unsigned umask = __reduce_or_sync(0xffffffffu, pend);
+          while (umask) {  // warp-uniform: one candidate column per turn
+            const int j = __ffs(umask) - 1;
+            umask &= umask - 1;
+            const float dot = __uint_as_float(ptx::tmem_ld1(taddr + (uint32_t)j));
+            ptx::tmem_wait_ld();
+            const float sc = score(dot, sdc[j]);
+            if (sc > thr) {  // rows arrive in ascending order: strict '>' keeps the lower index
+              top.insert(sc, row0 + chunk * 32 + j);
+              thr = top.threshold();
+            }
           }
         }
       }
