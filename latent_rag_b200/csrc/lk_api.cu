@@ -101,6 +101,10 @@ int check_device(int device, int* sm_count) {
   return LK_OK;
 }
 
+// row blocks allocated for `rows` rows: whole PAIRS of blocks, because the tcgen05 kernel
+// consumes two blocks per unit (the padding block is zeros with NaN side values)
+inline int64_t alloc_blocks(int64_t rows) { return (rows + 2 * kBlockRows - 1) / (2 * kBlockRows) * 2; }
+
 constexpr int64_t kStageRows = 1 << 16;  // rows staged per step when the input is on the host
 
 }  // namespace
@@ -201,7 +205,7 @@ int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, 
   ix->capacity = capacity_rows;
   ix->side_mode = ix->kmetric == LK_COSINE ? 0 : 1;
   ix->prenorm = (ix->kmetric == LK_COSINE && storage == LK_F32) ? 1 : 0;
-  const int64_t nblk = (capacity_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t nblk = alloc_blocks(capacity_rows);
   const size_t tile_bytes = (size_t)nblk * ix->g.block_bytes();
   const size_t side_bytes = (size_t)nblk * kBlockRows * sizeof(float);
 #define LK_CREATE_CUDA(expr)                                              \
@@ -297,8 +301,8 @@ int lk_index_reserve(lk_index* ix, int64_t capacity_rows) {
   }
   if (capacity_rows <= ix->capacity) return LK_OK;
   DeviceGuard guard(ix->device);
-  const int64_t old_blk = (ix->capacity + kBlockRows - 1) / kBlockRows;
-  const int64_t new_blk = (capacity_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t old_blk = alloc_blocks(ix->capacity);
+  const int64_t new_blk = alloc_blocks(capacity_rows);
   const size_t bb = (size_t)ix->g.block_bytes();
   unsigned char* tiles = nullptr;
   float* side = nullptr;

@@ -6,19 +6,19 @@
 // matrix only ever exists as 128x128 fp32 tiles in tensor memory.
 //
 // Shape of the computation
-//   unit       = (query tile of 128 queries) x (row block of 128 corpus rows)
+//   unit       = (query tile of 128 queries) x (PAIR of row blocks = 256 corpus rows)
 //   D[q][row]  = sum_k Q[q][k] * E[row][k]       tcgen05.mma M=128 (queries -> TMEM lanes)
-//                                                 N=128 (rows -> TMEM columns), K=16/instr
+//                                                 N=256 (rows -> TMEM columns), K=16/instr
 //   CTA c owns the contiguous unit range [c*U/G, (c+1)*U/G) of the query-tile-major unit
 //   order, so a CTA changes query tile at most once when there are <= G query tiles and
 //   CTAs whose ranges start at the same corpus offset share the row blocks through L2.
 //
 // Warp roles (384 threads, 1 CTA / SM)
-//   warp 0      TMA producer: 16 KB cp.async.bulk per (row block, K block of 64) into a
-//               ring of shared-memory stages; also brings the query tile in
-//   warp 1      MMA issuer (one thread): 4 tcgen05.mma per K block, accumulating a unit
-//               in one of 4 TMEM stages of 128 columns; tcgen05.commit frees smem stages
-//               and publishes finished accumulators
+//   warp 0      TMA producer: two 16 KB cp.async.bulk (one per row block) per K block of 64
+//               into a ring of 32 KB shared-memory stages; also brings the query tile in
+//   warp 1      MMA issuer (one elected lane): 4 tcgen05.mma (128x256x16) per K block,
+//               accumulating a unit in one of 2 TMEM stages of 256 columns; tcgen05.commit
+//               frees smem stages and publishes finished accumulators
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue: TMEM lane = query, so each thread owns ONE query (for half of
 //               the columns) and keeps its running top-k in registers: tcgen05.ld 32
@@ -41,9 +41,11 @@ constexpr int kThreads = 384;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kColSplit = kEpiWarps / 4;                 // epilogue warps per lane quarter
-constexpr int kColsPerWarp = kBlockRows / kColSplit;     // 64 columns of each accumulator
-constexpr int kAccStages = 4;                            // 4 x 128 columns = all of TMEM
-constexpr int kTmemCols = kAccStages * kBlockRows;       // 512
+constexpr int kUnitBlocks = 2;                           // row blocks per unit
+constexpr int kUnitCols = kUnitBlocks * kBlockRows;      // 256 accumulator columns per unit
+constexpr int kColsPerWarp = kUnitCols / kColSplit;      // 128: one row block per epilogue warp
+constexpr int kAccStages = 2;                            // 2 x 256 columns = all of TMEM
+constexpr int kTmemCols = kAccStages * kUnitCols;        // 512
 constexpr int kKBlockElems = kRowBytes / 2;              // 64 bf16 per row per K block
 constexpr int kKBlockBytes = kSlabBytes;                 // 16384
 constexpr int kMaxStages = 8;
@@ -66,7 +68,7 @@ struct UmmaParams {
   const float* q_side;
   int64_t n_queries;
   int64_t total_units;   // n_qt * nblk
-  int nblk;              // row blocks in the corpus
+  int nblk;              // row-block PAIRS in the corpus (units per query tile)
   int nkb;               // K blocks of 64 per row
   int n_stages;
   int n_lists;
@@ -115,9 +117,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   unsigned char* q_sm = smem + kHeaderBytes;
   q_sm += (1024u - (ptx::smem_u32(q_sm) & 1023u)) & 1023u;  // swizzle atoms are 1024-byte aligned
   unsigned char* stage_sm = q_sm + (QRES ? p.nkb * kKBlockBytes : 0);
-  constexpr int kStageBytes = QRES ? kKBlockBytes : 2 * kKBlockBytes;
+  constexpr int kStageBytes = (QRES ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int64_t G = gridDim.x, c = blockIdx.x;
   const int64_t u0 = unit_begin(c, p.total_units, G), u1 = unit_begin(c + 1, p.total_units, G);
 
@@ -145,100 +148,114 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   const uint32_t tmem_base = *tmem_ptr_s;
 
   auto fail = [&](int code) {
-    atomicCAS(p.err_flag, 0, code);
+    if (lane == 0) atomicCAS(p.err_flag, 0, code);
     *abort_s = 1;
   };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      Ring st;
-      int seg = 0;
-      int64_t u = u0;
-      int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
-      bool ok = true;
-      for (; u < u1 && ok; ++u) {
-        const unsigned char* q_src = p.q_tiles + (int64_t)qt * p.block_bytes;
-        if (QRES && (u == u0 || b == 0)) {
-          if (seg > 0 && !ptx::mbar_wait(qempty_bar, (uint32_t)((seg - 1) & 1))) {
-            fail(kErrProdQEmpty);
-            break;
-          }
+    // The whole warp runs the loop with warp-uniform values (so they live in uniform
+    // registers); one elected lane issues the copies.
+    Ring st;
+    int seg = 0;
+    int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
+    bool ok = true;
+    for (int64_t u = u0; u < u1 && ok; ++u) {
+      const unsigned char* q_src = p.q_tiles + (int64_t)qt * p.block_bytes;
+      if (QRES && (u == u0 || b == 0)) {
+        if (seg > 0 && !__all_sync(0xffffffffu, ptx::mbar_wait(qempty_bar, (uint32_t)((seg - 1) & 1)))) {
+          fail(kErrProdQEmpty);
+          break;
+        }
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(p.nkb * kKBlockBytes));
           for (int kb = 0; kb < p.nkb; ++kb)
             ptx::bulk_g2s(ptx::smem_u32(q_sm + kb * kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
                           kKBlockBytes, qfull_bar);
-          ++seg;
         }
-        const unsigned char* e_src = p.tiles + (int64_t)b * p.block_bytes;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          if (!ptx::mbar_wait(empty_bar(st.idx), st.phase ^ 1u)) {
-            fail(kErrProdEmpty);
-            ok = false;
-            break;
-          }
-          unsigned char* dst = stage_sm + st.idx * kStageBytes;
+        __syncwarp();
+        ++seg;
+      }
+      const unsigned char* e_src = p.tiles + (int64_t)b * kUnitBlocks * p.block_bytes;
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(empty_bar(st.idx), st.phase ^ 1u))) {
+          fail(kErrProdEmpty);
+          ok = false;
+          break;
+        }
+        if (ptx::elect_one()) {
+          const uint32_t dst = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
           ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
-          ptx::bulk_g2s(ptx::smem_u32(dst), e_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
-                        full_bar(st.idx));
-          if (!QRES)
-            ptx::bulk_g2s(ptx::smem_u32(dst + kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
+#pragma unroll
+          for (int h = 0; h < kUnitBlocks; ++h)  // rows 0-127 and 128-255 of the N=256 operand
+            ptx::bulk_g2s(dst + h * kKBlockBytes, e_src + h * p.block_bytes + (int64_t)kb * kKBlockBytes,
                           kKBlockBytes, full_bar(st.idx));
-          st.advance(p.n_stages);
+          if (!QRES)
+            ptx::bulk_g2s(dst + kUnitBlocks * kKBlockBytes, q_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
+                          full_bar(st.idx));
         }
-        if (++b == p.nblk) {
-          b = 0;
-          ++qt;
-        }
+        __syncwarp();
+        st.advance(p.n_stages);
+      }
+      if (++b == p.nblk) {
+        b = 0;
+        ++qt;
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockRows, kBlockRows);
-      Ring st, acc;
-      int seg = 0;
-      int b = (int)(u0 % p.nblk);
-      bool ok = true;
-      for (int64_t u = u0; u < u1 && ok; ++u) {
-        if (!ptx::mbar_wait(tempty_bar(acc.idx), acc.phase ^ 1u)) {
-          fail(kErrMmaTmemEmpty);
+    // Warp-uniform loop; one elected lane issues the 4 tcgen05.mma of a K block and the
+    // commits.  Descriptors differ only in the 14-bit start-address field.
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockRows, kUnitCols);
+    const uint64_t desc_hi = ptx::smem_desc(0, p.lbo, p.sbo);
+    const uint32_t q_base = ptx::smem_u32(q_sm) >> 4, st_base = ptx::smem_u32(stage_sm) >> 4;
+    Ring st, acc;
+    int seg = 0;
+    int b = (int)(u0 % p.nblk);
+    bool ok = true;
+    for (int64_t u = u0; u < u1 && ok; ++u) {
+      if (!__all_sync(0xffffffffu, ptx::mbar_wait(tempty_bar(acc.idx), acc.phase ^ 1u))) {
+        fail(kErrMmaTmemEmpty);
+        break;
+      }
+      if (QRES && (u == u0 || b == 0)) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1)))) {
+          fail(kErrMmaQFull);
           break;
         }
-        if (QRES && (u == u0 || b == 0)) {
-          if (!ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1))) {
-            fail(kErrMmaQFull);
-            break;
-          }
-          ++seg;
+        ++seg;
+      }
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc.idx * kUnitCols);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(full_bar(st.idx), st.phase))) {
+          fail(kErrMmaFull);
+          ok = false;
+          break;
         }
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc.idx * kBlockRows);
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          if (!ptx::mbar_wait(full_bar(st.idx), st.phase)) {
-            fail(kErrMmaFull);
-            ok = false;
-            break;
-          }
-          ptx::tc_fence_after();
-          const uint32_t e_addr = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
-          const uint32_t q_addr = QRES ? ptx::smem_u32(q_sm + kb * kKBlockBytes) : e_addr + kKBlockBytes;
+        const uint32_t e_lo = st_base + (uint32_t)(st.idx * (kStageBytes >> 4));
+        const uint32_t q_lo = QRES ? q_base + (uint32_t)(kb * (kKBlockBytes >> 4))
+                                   : e_lo + (uint32_t)(kUnitBlocks * (kKBlockBytes >> 4));
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kKBlockElems / 16; ++k) {
-            const uint32_t off = (uint32_t)k * kUmmaKBytes;  // advance inside the 128-byte swizzled row
-            ptx::umma_bf16(d_tmem, ptx::smem_desc(q_addr + off, p.lbo, p.sbo),
-                           ptx::smem_desc(e_addr + off, p.lbo, p.sbo), idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kKBlockElems / 16; ++k)  // +32 bytes per K step inside the swizzled row
+            ptx::umma_bf16(d_tmem, desc_hi | (uint64_t)((q_lo + 2u * k) & 0x3fffu),
+                           desc_hi | (uint64_t)((e_lo + 2u * k) & 0x3fffu), idesc, (kb | k) != 0 ? 1u : 0u);
           ptx::umma_commit(empty_bar(st.idx));  // smem stage reusable once these MMAs retire
-          st.advance(p.n_stages);
         }
-        if (!ok) break;
-        ptx::umma_commit(tfull_bar(acc.idx));   // accumulator complete -> epilogue
-        acc.advance(kAccStages);
-        const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
-        if (QRES && seg_end) ptx::umma_commit(qempty_bar);  // query tile no longer read
-        if (++b == p.nblk) b = 0;
+        __syncwarp();
+        st.advance(p.n_stages);
       }
+      if (!ok) break;
+      const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
+      if (ptx::elect_one()) {
+        ptx::umma_commit(tfull_bar(acc.idx));              // accumulator complete -> epilogue
+        if (QRES && seg_end) ptx::umma_commit(qempty_bar);  // query tile no longer read
+      }
+      __syncwarp();
+      acc.advance(kAccStages);
+      if (++b == p.nblk) b = 0;
     }
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue: metric + running top-k =====================
@@ -256,9 +273,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     float q_sd = 0.f;
     bool seg_start = true;
     if (u0 < u1) {
-      const float* sp = p.side + (int64_t)b * kBlockRows + ch * kColsPerWarp;
-      my_side[lane] = sp[lane];
-      my_side[lane + 32] = sp[lane + 32];
+      const float* sp = p.side + (int64_t)b * kUnitCols + ch * kColsPerWarp;
+#pragma unroll
+      for (int j = 0; j < kColsPerWarp / 32; ++j) my_side[lane + 32 * j] = sp[lane + 32 * j];
       __syncwarp();
     }
     for (int64_t u = u0; u < u1; ++u) {
@@ -275,19 +292,21 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         nb = 0;
         ++nqt;
       }
-      float ns0 = 0.f, ns1 = 0.f;
+      float ns[kColsPerWarp / 32];
+#pragma unroll
+      for (int j = 0; j < kColsPerWarp / 32; ++j) ns[j] = 0.f;
       if (u + 1 < u1) {
-        const float* sp = p.side + (int64_t)nb * kBlockRows + ch * kColsPerWarp;
-        ns0 = sp[lane];
-        ns1 = sp[lane + 32];
+        const float* sp = p.side + (int64_t)nb * kUnitCols + ch * kColsPerWarp;
+#pragma unroll
+        for (int j = 0; j < kColsPerWarp / 32; ++j) ns[j] = sp[lane + 32 * j];
       }
-      if (!ptx::mbar_wait(tfull_bar(acc.idx), acc.phase)) {
-        if (lane == 0) fail(kErrEpiTmemFull);
+      if (!__all_sync(0xffffffffu, ptx::mbar_wait(tfull_bar(acc.idx), acc.phase))) {
+        fail(kErrEpiTmemFull);
         break;
       }
       ptx::tc_fence_after();
       const float* sd = my_side + slot * kColsPerWarp;
-      const int32_t row0 = b * kBlockRows + ch * kColsPerWarp;
+      const int32_t row0 = b * kUnitCols + ch * kColsPerWarp;
       // Fast path (branch-free, a few hundred instructions in total so it stays in the
       // instruction cache): score every column and keep the running max.  Only when some
       // lane's max beats its k-th best does the warp take the slow path, which holds the
@@ -296,13 +315,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)(acc.idx * kBlockRows + ch * kColsPerWarp + chunk * 32);
+                               (uint32_t)(acc.idx * kUnitCols + ch * kColsPerWarp + chunk * 32);
         ptx::tmem_ld32(taddr, r);
         ptx::tmem_wait_ld();
         if (p.debug_tile != nullptr && u == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            p.debug_tile[lane_q * kBlockRows + ch * kColsPerWarp + chunk * 32 + j] = __uint_as_float(r[j]);
+            if (ch == 0) p.debug_tile[lane_q * kBlockRows + chunk * 32 + j] = __uint_as_float(r[j]);
         }
         const float* sdc = sd + chunk * 32;
         auto score = [&](float dot, float e_sd) -> float {
@@ -336,8 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc.idx));
       acc.advance(kAccStages);
       slot ^= 1;
-      my_side[slot * kColsPerWarp + lane] = ns0;
-      my_side[slot * kColsPerWarp + lane + 32] = ns1;
+#pragma unroll
+      for (int j = 0; j < kColsPerWarp / 32; ++j) my_side[slot * kColsPerWarp + lane + 32 * j] = ns[j];
       __syncwarp();
 
       const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
@@ -372,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 inline int n_kblocks(const TileGeom& g) { return g.kblocks; }
 inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
 inline int n_stages_for(const TileGeom& g) {
-  const int stage = q_resident(g) ? kKBlockBytes : 2 * kKBlockBytes;
+  const int stage = (q_resident(g) ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
   const int q_bytes = q_resident(g) ? n_kblocks(g) * kKBlockBytes : 0;
   int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage;
   return s > kMaxStages ? kMaxStages : s;
@@ -386,7 +405,7 @@ int umma_supported(const TileGeom& g, int k) {
 }
 
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
-  const int64_t nblk = (a.n_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t nblk = (a.n_rows + kUnitCols - 1) / kUnitCols;  // units (row-block pairs) per query tile
   const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
   const int64_t total = nblk * nqt;
   const int64_t grid = total < sm_count ? total : sm_count;
@@ -406,7 +425,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     set_error("tcgen05 search: unsupported shape (dim_pad=%d, k=%d)", a.g.dim_pad, a.k);
     return LK_ERR_UNSUPPORTED;
   }
-  const int64_t nblk = (a.n_rows + kBlockRows - 1) / kBlockRows;
+  const int64_t nblk = (a.n_rows + kUnitCols - 1) / kUnitCols;  // units (row-block pairs) per query tile
   const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
   UmmaParams p;
   p.tiles = static_cast<const unsigned char*>(a.tiles);
@@ -429,7 +448,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
   if (const char* e = getenv("LK_UMMA_SBO")) p.sbo = (uint32_t)atoi(e);
   const bool qres = q_resident(a.g);
-  const int stage = qres ? kKBlockBytes : 2 * kKBlockBytes;
+  const int stage = (qres ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
   const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
                       (size_t)p.n_stages * stage;
   const int64_t grid = p.total_units < sm_count ? p.total_units : sm_count;
