@@ -51,6 +51,16 @@ def parse_args():
     return ap.parse_args()
 
 
+def traffic_ratios():
+    """measured DRAM bytes / algorithmic bytes of the search kernel (ncu, profiles/r01_traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["batch1"]["ratio"]), float(t["batch4096"]["ratio"])
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -313,6 +323,7 @@ def main():
         ach_tf = flops / (kms * 1e-3) / 1e12
         ach_gbs1 = bytes_per_launch / (kms1 * 1e-3) / 1e9
         base = cpu_baseline(args, 3, 1) if world == 1 else None
+        r1, r4096 = traffic_ratios()
         line = {
             "metric": METRIC_NAME, "value": args.batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
@@ -322,7 +333,8 @@ def main():
                     "h2d_bytes_per_step": int(q_pin.numel() * 4), "d2h_bytes_per_step": int(args.batch * k * 12)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": pk["bf16_tflops_sustained"],
-                         "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops_sustained"], "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach_tf / pk["bf16_tflops_sustained"],
+                         "traffic": None if r4096 is None else r4096 * bytes_per_launch,
                          "kernel": "umma_search_kernel", "kernel_ms": kms, "flops_per_launch": flops,
                          "peak_src": pk["src"] + " sustained bf16 (kernel runs for hundreds of ms per launch)",
                          "frac_of_burst_peak": ach_tf / pk["bf16_tflops"]},
@@ -330,7 +342,8 @@ def main():
                        "e2e": {"value": 1.0 / (ms1_e2e * 1e-3), "unit": UNIT, "ms_per_query": ms1_e2e,
                                "h2d_bytes_per_step": args.dim * 4, "d2h_bytes_per_step": k * 12},
                        "roofline": {"bound": "hbm", "achieved": ach_gbs1, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                    "frac": ach_gbs1 / pk["hbm_gbs"], "traffic": None, "kernel_ms": kms1,
+                                    "frac": ach_gbs1 / pk["hbm_gbs"],
+                                    "traffic": None if r1 is None else r1 * bytes_per_launch, "kernel_ms": kms1,
                                     "bytes_per_launch": bytes_per_launch, "peak_src": pk["src"]}},
             "clocks": clocks,
             "checks": {"planted_neighbours_found": planted_ok, "scores_sorted": sorted_ok,
