@@ -404,7 +404,7 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (b == 0) return LK_OK;
   const int which = pick_kernel(ix, kernel, k);
   if (which == LK_KERNEL_UMMA && !umma_supported(ix->g, k)) {
-    set_error("lk_index_search: the tcgen05 kernel needs bf16 storage and k <= 32 (k=%d, storage=%d)", k,
+    set_error("lk_index_search: the tcgen05 kernel needs bf16 storage (k=%d, storage=%d)", k,
               ix->storage);
     return LK_ERR_UNSUPPORTED;
   }

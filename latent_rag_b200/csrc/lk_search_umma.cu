@@ -73,7 +73,8 @@ struct UmmaParams {
   int n_stages;
   int n_lists;
   int64_t block_bytes;
-  float* part_scores;    // [n_queries, n_lists, KSEL]
+  int ksel;              // entries per partial list (KSEL, or k for the heap selector)
+  float* part_scores;    // [n_queries, n_lists, ksel]
   int32_t* part_idx;
   int* err_flag;
   float* debug_tile;     // [128 queries][128 rows] raw dot products of unit 0, or null
@@ -267,9 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     Ring acc;
     int slot = 0;
     int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
-    RegTopK<KSEL> top;
-    top.init();
-    float thr = top.threshold();
+    typename SelectorFor<KSEL>::type top;
+    float thr = INFINITY;
     float q_sd = 0.f;
     bool seg_start = true;
     if (u0 < u1) {
@@ -281,8 +281,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     for (int64_t u = u0; u < u1; ++u) {
       if (seg_start) {
         const int64_t q = (int64_t)qt * kBlockRows + lane_q;
-        q_sd = q < p.n_queries ? p.q_side[q] : 0.f;
-        top.init();
+        const bool q_ok = q < p.n_queries;
+        q_sd = q_ok ? p.q_side[q] : 0.f;
+        const int64_t c_first = cta_of_unit((int64_t)qt * p.nblk, p.total_units, G);
+        const int list = (int)(c - c_first) * kColSplit + ch;
+        const int64_t o = q_ok ? (q * p.n_lists + list) * p.ksel : 0;
+        top.begin(p.part_scores + o, p.part_idx + o, q_ok, p.ksel);
         thr = top.threshold();
         seg_start = false;
       }
@@ -361,17 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 
       const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
       if (seg_end) {
-        const int64_t q = (int64_t)qt * kBlockRows + lane_q;
-        if (q < p.n_queries) {
-          const int64_t c_first = cta_of_unit((int64_t)qt * p.nblk, p.total_units, G);
-          const int list = (int)(c - c_first) * kColSplit + ch;
-          const int64_t o = (q * p.n_lists + list) * KSEL;
-#pragma unroll
-          for (int j = 0; j < KSEL; ++j) {
-            p.part_scores[o + j] = METRIC == LK_COSINE ? top.s[j] * q_sd : top.s[j];
-            p.part_idx[o + j] = top.ix[j];
-          }
-        }
+        top.finish(q_sd, METRIC == LK_COSINE, p.ksel);  // cosine: x 1/|q| once per kept entry
         seg_start = true;
       }
       b = nb;
@@ -396,12 +390,12 @@ inline int n_stages_for(const TileGeom& g) {
   int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage;
   return s > kMaxStages ? kMaxStages : s;
 }
-inline int ksel_for(int k) { return k <= 10 ? 10 : 32; }
+inline int ksel_for(int k) { return k <= 10 ? 10 : (k <= 32 ? 32 : k); }  // > 32: heap of exactly k
 
 }  // namespace
 
 int umma_supported(const TileGeom& g, int k) {
-  return g.elem_bytes == 2 && g.kblocks >= 1 && k >= 1 && k <= 32 && n_stages_for(g) >= 2;
+  return g.elem_bytes == 2 && g.kblocks >= 1 && k >= 1 && k <= kMaxK && n_stages_for(g) >= 2;
 }
 
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
@@ -438,6 +432,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.nkb = n_kblocks(a.g);
   p.n_stages = n_stages_for(a.g);
   p.n_lists = a.n_lists;
+  p.ksel = a.ksel;
   p.block_bytes = a.g.block_bytes();
   p.part_scores = a.part_scores;
   p.part_idx = a.part_idx;
@@ -470,8 +465,10 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   } while (0)
   if (ksel == 10) {
     if (qres) LK_UMMA_M(10, true); else LK_UMMA_M(10, false);
-  } else {
+  } else if (ksel == 32) {
     if (qres) LK_UMMA_M(32, true); else LK_UMMA_M(32, false);
+  } else {
+    if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);
   }
 #undef LK_UMMA_M
 #undef LK_UMMA

@@ -115,4 +115,85 @@ struct RegTopK {
   }
 };
 
+// Selector interfaces used by the tcgen05 epilogue (one thread = one query):
+//   begin(list_scores, list_idx, valid)  start a (query, partial-list) segment
+//   threshold() / insert(score, id)      running top-k (insert requires score > threshold())
+//   finish(scale)                        leave the list in list_scores / list_idx
+template <int K>
+struct RegSelector {
+  RegTopK<K> top;
+  float* out_s;
+  int32_t* out_i;
+  bool valid;
+  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int /*k*/) {
+    out_s = s; out_i = ix; valid = v;
+    top.init();
+  }
+  __device__ __forceinline__ float threshold() const { return top.threshold(); }
+  __device__ __forceinline__ void insert(float v, int32_t id) { top.insert(v, id); }
+  __device__ __forceinline__ void finish(float scale, bool apply_scale, int /*k*/) {
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      out_s[j] = apply_scale ? top.s[j] * scale : top.s[j];
+      out_i[j] = top.ix[j];
+    }
+  }
+};
+
+// k up to 128: a binary heap (root = worst kept entry) living directly in the thread's
+// partial-list slot in global memory (L2-resident; touched only on the rare insert).
+struct HeapSelector {
+  float* hs;
+  int32_t* hi;
+  float thr;
+  bool valid;
+  int k;
+  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int kk) {
+    hs = s; hi = ix; valid = v; k = kk;
+    thr = v ? -INFINITY : INFINITY;  // lanes without a query never insert
+    if (v)
+      for (int j = 0; j < kk; ++j) {
+        hs[j] = -INFINITY;
+        hi[j] = 0x7fffffff;
+      }
+  }
+  __device__ __forceinline__ float threshold() const { return thr; }
+  // precondition: v > thr (rows arrive in ascending index order)
+  __device__ __forceinline__ void insert(float v, int32_t id) {
+    int i = 0;
+    for (;;) {
+      const int l = 2 * i + 1;
+      if (l >= k) break;
+      int c = l;
+      float sc = hs[l];
+      int32_t ic = hi[l];
+      if (l + 1 < k) {  // descend towards the WORSE child: lower score, higher index on ties
+        const float sr = hs[l + 1];
+        const int32_t ir = hi[l + 1];
+        if (sr < sc || (sr == sc && ir > ic)) {
+          c = l + 1; sc = sr; ic = ir;
+        }
+      }
+      if (sc < v || (sc == v && ic > id)) {  // child is worse than the new entry: move it up
+        hs[i] = sc;
+        hi[i] = ic;
+        i = c;
+      } else {
+        break;
+      }
+    }
+    hs[i] = v;
+    hi[i] = id;
+    thr = hs[0];
+  }
+  __device__ __forceinline__ void finish(float scale, bool apply_scale, int kk) {
+    if (!valid || !apply_scale) return;
+    for (int j = 0; j < kk; ++j) hs[j] *= scale;
+  }
+};
+
+template <int KSEL> struct SelectorFor { using type = RegSelector<KSEL>; };
+template <> struct SelectorFor<0> { using type = HeapSelector; };
+
 }  // namespace lk

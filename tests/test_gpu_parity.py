@@ -125,6 +125,11 @@ SHAPES = [
     (3000, 200, 768, 30),
     (40000, 1, 384, 10),
     (2500, 1500, 64, 10),
+    # k > 32: per-thread heap selector
+    (3000, 40, 768, 100),
+    (20000, 150, 384, 128),
+    (500, 7, 64, 64),
+    (300, 3, 32, 100),
 ]
 
 
@@ -133,7 +138,7 @@ SHAPES = [
 def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
     """tcgen05 kernel over ragged shapes: partial row blocks, partial query tiles, several
     query tiles per CTA range, K padding (dim 32/100), streamed-Q (dim 768), k in both
-    register-list sizes."""
+    register-list sizes and in the heap selector (k > 32)."""
     monkeypatch.setenv("LK_FORCE_KERNEL", "umma")
     rng = np.random.default_rng(n * 7 + b)
     emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
