@@ -122,6 +122,12 @@ int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx,
  *      w0 [d_hidden x d_in], b0 [d_hidden], w1 [d_latent x d_hidden], b1 [d_latent]. */
 int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int d_latent,
                  const float* w0, const float* b0, const float* w1, const float* b1);
+/* LK_KERNEL_UMMA: tensor-core kernel with split-bf16 operands (x = hi + lo, three MMAs per
+ * product, fp32 accumulate; ~1e-5 of the row scale), available when d_in % 64 == 0,
+ * d_hidden % 128 == 0 and d_latent <= 64; LK_KERNEL_SIMT: fp32 FMA kernel (any dims, the
+ * reference's arithmetic); LK_KERNEL_AUTO (default): UMMA for calls of >= 256 rows when
+ * available, SIMT otherwise. */
+int lk_ae_set_kernel(lk_ae* ae, int kernel);
 /* x: m x d_in fp32 row-major; z: m x d_latent fp32 row-major */
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream);
 int lk_ae_destroy(lk_ae* ae);

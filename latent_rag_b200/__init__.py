@@ -3,6 +3,7 @@ forward behind latent-rag's retriever API.  Hand-written sm_100a CUDA (liblatent
 called through a C ABI; Python/PyTorch only for device memory, streams and
 torch.distributed.  No CPU fallback."""
 from . import _native
+from ._native import NativeError
 from .engine import ExactIndex, merge_topk
 from .retrieval import BruteForceRetriever, FAISSEmbeddingRetriever, StatsTracker, build_retriever
 from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, VariationalAutoencoder,
@@ -12,5 +13,5 @@ from .sharded import ShardedRetriever, shard_bounds
 __all__ = [
     "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
-    "load_autoencoder", "ShardedRetriever", "shard_bounds",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError",
 ]

@@ -33,6 +33,7 @@ class _FusedEncoder:
         self._h = c_void_p()
         self._lib = None
         self._weights: Optional[Dict[str, np.ndarray]] = None
+        self._kernel = "auto"
         self.training = False
 
     # -- nn.Module-shaped surface used by the reference pipeline -----------------------
@@ -66,6 +67,17 @@ class _FusedEncoder:
         self._release()
         return self
 
+    def set_kernel(self, kernel: str):
+        """"auto" (tensor cores for batches of >= 256 rows when the dims allow, fp32 FMA otherwise),
+        "umma" (split-bf16 tcgen05 kernel: 3 MMAs per product, ~1e-5 of the row scale) or
+        "simt" (fp32 FMA kernel, the reference's arithmetic)."""
+        if kernel not in nat.KERNELS:
+            raise ValueError(f"Unknown kernel: {kernel}")
+        self._kernel = kernel
+        if self._h:
+            nat.check(self._lib.lk_ae_set_kernel(self._h, nat.KERNELS[kernel]), "lk_ae_set_kernel")
+        return self
+
     # -- native handle -------------------------------------------------------------------
     def _release(self):
         if self._h:
@@ -94,6 +106,8 @@ class _FusedEncoder:
                                    c_void_p(w["w1"].ctypes.data), c_void_p(w["b1"].ctypes.data)),
             "lk_ae_create",
         )
+        if self._kernel != "auto":
+            nat.check(self._lib.lk_ae_set_kernel(self._h, nat.KERNELS[self._kernel]), "lk_ae_set_kernel")
         return self._h
 
     def _encode(self, x: torch.Tensor) -> torch.Tensor:

@@ -12,6 +12,8 @@
 #include "lk_common.cuh"
 
 namespace lk {
+void ae_umma_weight_slabs(const float* w, int rows_out, int k_in, int slab_rows, std::vector<unsigned char>* out,
+                          bool plane_major_over_kb_only);
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -129,10 +131,13 @@ struct lk_index {
 };
 
 struct lk_ae {
-  int device = 0;
+  int device = 0, sm_count = 0;
   int kind = 0, d_in = 0, d_hidden = 0, d_latent = 0;
+  int kernel = LK_KERNEL_AUTO;  // AUTO/UMMA: split-bf16 tensor-core kernel when the dims allow; SIMT: fp32 FMA
   float *w0t = nullptr, *b0 = nullptr, *w1t = nullptr, *b1 = nullptr;
-  Buf xin, zout;
+  unsigned char *w0_slabs = nullptr, *w1_slabs = nullptr;
+  int* err_flag = nullptr;
+  Buf xin, zout, xslabs;
 };
 
 extern "C" {
@@ -562,8 +567,12 @@ int lk_ae_destroy(lk_ae* ae) {
   float* ps[] = {ae->w0t, ae->b0, ae->w1t, ae->b1};
   for (float* p : ps)
     if (p) cudaFree(p);
+  if (ae->w0_slabs) cudaFree(ae->w0_slabs);
+  if (ae->w1_slabs) cudaFree(ae->w1_slabs);
+  if (ae->err_flag) cudaFree(ae->err_flag);
   ae->xin.release();
   ae->zout.release();
+  ae->xslabs.release();
   delete ae;
   return LK_OK;
 }
@@ -584,6 +593,7 @@ int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int 
   lk_ae* ae = new (std::nothrow) lk_ae();
   if (!ae) return LK_ERR_OOM;
   ae->device = device;
+  ae->sm_count = sm;
   ae->kind = kind;
   ae->d_in = d_in;
   ae->d_hidden = d_hidden;
@@ -607,7 +617,34 @@ int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int 
       return rc;
     }
   }
+  if (ae_umma_supported(d_in, d_hidden, d_latent)) {
+    // split-bf16 weight planes in the tcgen05 slab format
+    std::vector<unsigned char> s0, s1;
+    ae_umma_weight_slabs(w0, d_hidden, d_in, kBlockRows, &s0, false);
+    ae_umma_weight_slabs(w1, d_latent, d_hidden, round_up(d_latent, 16), &s1, true);
+    cudaError_t e = cudaMalloc((void**)&ae->w0_slabs, s0.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ae->w1_slabs, s1.size());
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ae->err_flag, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(ae->w0_slabs, s0.data(), s0.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ae->w1_slabs, s1.data(), s1.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(ae->err_flag, 0, sizeof(int));
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "ae weight slab upload", __FILE__, __LINE__);
+      lk_ae_destroy(ae);
+      return rc;
+    }
+  }
   *out = ae;
+  return LK_OK;
+}
+
+int lk_ae_set_kernel(lk_ae* ae, int kernel) {
+  if (!ae || kernel < LK_KERNEL_AUTO || kernel > LK_KERNEL_UMMA) return LK_ERR_INVALID;
+  if (kernel == LK_KERNEL_UMMA && !ae->w0_slabs) {
+    set_error("lk_ae_set_kernel: the tensor-core encoder needs d_in %% 64 == 0, d_hidden %% 128 == 0, d_latent <= 64");
+    return LK_ERR_UNSUPPORTED;
+  }
+  ae->kernel = kernel;
   return LK_OK;
 }
 
@@ -623,6 +660,12 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
   const int l2 = ae->kind == LK_AE_CAE ? 1 : 0;
   const int64_t step = 1 << 18;
   int rc;
+  // AUTO: tensor cores once there are two full row tiles of work, fp32 FMA for small batches
+  const char* env = getenv("LK_AE_KERNEL");
+  int which = ae->kernel;
+  if (env && !strcmp(env, "simt")) which = LK_KERNEL_SIMT;
+  if (env && !strcmp(env, "umma")) which = LK_KERNEL_UMMA;
+  const bool use_umma = ae->w0_slabs && (which == LK_KERNEL_UMMA || (which == LK_KERNEL_AUTO && m >= 2 * kBlockRows));
   for (int64_t done = 0; done < m; done += step) {
     const int64_t cnt = m - done < step ? m - done : step;
     const float* xin = x + (size_t)done * ae->d_in;
@@ -637,12 +680,30 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
       if ((rc = ae->zout.ensure((size_t)step * ae->d_latent * 4)) != LK_OK) return rc;
       zdev = ae->zout.as<float>();
     }
-    rc = launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1,
-                          l2, zdev, st);
+    if (use_umma) {
+      if ((rc = ae->xslabs.ensure(ae_umma_x_slab_bytes(step, ae->d_in))) != LK_OK) return rc;
+      if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;
+      rc = launch_ae_umma(ae->xslabs.as<unsigned char>(), cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs,
+                          ae->w1_slabs, ae->b0, ae->b1, l2, zdev, ae->err_flag, ae->sm_count, st);
+    } else {
+      rc = launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1,
+                            l2, zdev, st);
+    }
     if (rc != LK_OK) return rc;
     if (z_mem == LK_HOST)
       LK_CUDA(cudaMemcpyAsync(zo, zdev, (size_t)cnt * ae->d_latent * 4, cudaMemcpyDeviceToHost, st));
-    if (x_mem == LK_HOST || z_mem == LK_HOST) LK_CUDA(cudaStreamSynchronize(st));
+    if (x_mem == LK_HOST || z_mem == LK_HOST) {
+      LK_CUDA(cudaStreamSynchronize(st));
+      if (ae->err_flag) {
+        int flag = 0;
+        LK_CUDA(cudaMemcpy(&flag, ae->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag != 0) {
+          cudaMemset(ae->err_flag, 0, sizeof(int));
+          set_error("autoencoder kernel pipeline timed out (barrier code %d); results are invalid", flag);
+          return LK_ERR_CUDA;
+        }
+      }
+    }
   }
   return LK_OK;
 }
