@@ -124,7 +124,7 @@ struct lk_index {
   float* side = nullptr;
   double* whiten = nullptr;
   int* err_flag = nullptr;
-  Buf stage, white, q_tiles, q_side, part_s, part_i, out_s, out_i, debug;
+  Buf stage, white, q_tiles, q_side, part_s, part_i, part_c, out_s, out_i, debug;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_search_ms = 0.f, last_total_ms = 0.f;
@@ -166,7 +166,8 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->side) cudaFree(ix->side);
   if (ix->whiten) cudaFree(ix->whiten);
   if (ix->err_flag) cudaFree(ix->err_flag);
-  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->out_s, &ix->out_i, &ix->debug};
+  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->part_c,
+                 &ix->out_s, &ix->out_i, &ix->debug};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : ix->ev)
     if (e) cudaEventDestroy(e);
@@ -440,6 +441,7 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   a.metric = ix->kmetric;
   a.k = k;
   a.err_flag = ix->err_flag;
+  a.seed = nullptr;
   a.debug_tile = nullptr;
   const char* dump_path = which == LK_KERNEL_UMMA ? getenv("LK_UMMA_DUMP") : nullptr;
   if (dump_path) {  // bring-up aid: raw accumulator of unit 0 -> file
@@ -450,16 +452,53 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   if (rc != LK_OK) return rc;
+  // results land here (device): the caller's buffers, or staging for a host copy
+  float* d_s = out_scores;
+  int64_t* d_i = out_idx;
+  if (out_mem == LK_HOST) {
+    if ((rc = ix->out_s.ensure((size_t)b * k * sizeof(float))) != LK_OK) return rc;
+    if ((rc = ix->out_i.ensure((size_t)b * k * sizeof(int64_t))) != LK_OK) return rc;
+    d_s = ix->out_s.as<float>();
+    d_i = ix->out_i.as<int64_t>();
+  }
+  const int merge_len = a.ksel > kMaxK ? a.ksel : (k < a.ksel ? k : a.ksel);
+  const int64_t seed_rows = which == LK_KERNEL_UMMA ? umma_seed_rows(a, ix->sm_count) : 0;
+  SearchArgs a0 = a;  // the seeding search over a prefix of the corpus
+  if (seed_rows > 0) {
+    a0.n_rows = seed_rows;
+    if ((rc = umma_plan(a0, ix->sm_count, &a0.n_lists, &a0.ksel)) != LK_OK) return rc;
+  }
   const size_t n_part = (size_t)b * a.n_lists * a.ksel;
-  if ((rc = ix->part_s.ensure(n_part * sizeof(float))) != LK_OK) return rc;
-  if ((rc = ix->part_i.ensure(n_part * sizeof(int32_t))) != LK_OK) return rc;
-  a.part_scores = ix->part_s.as<float>();
-  a.part_idx = ix->part_i.as<int32_t>();
-  LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
-  LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
+  const size_t n_part0 = seed_rows > 0 ? (size_t)b * a0.n_lists * a0.ksel : 0;
+  const size_t n_part_max = n_part > n_part0 ? n_part : n_part0;
+  if ((rc = ix->part_s.ensure(n_part_max * sizeof(float))) != LK_OK) return rc;
+  if ((rc = ix->part_i.ensure(n_part_max * sizeof(int32_t))) != LK_OK) return rc;
+  a.part_scores = a0.part_scores = ix->part_s.as<float>();
+  a.part_idx = a0.part_idx = ix->part_i.as<int32_t>();
+  a.part_cnt = a0.part_cnt = nullptr;
+  const bool counted = which == LK_KERNEL_UMMA && a.ksel > kMaxK;  // append buffers report their fill
+  const size_t n_cnt = (size_t)b * a.n_lists, n_cnt0 = seed_rows > 0 ? (size_t)b * a0.n_lists : 0;
+  if (counted) {
+    if ((rc = ix->part_c.ensure((n_cnt > n_cnt0 ? n_cnt : n_cnt0) * sizeof(int))) != LK_OK) return rc;
+    a.part_cnt = a0.part_cnt = ix->part_c.as<int>();
+  }
 
   // 3. fused distance + selection
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
+  if (seed_rows > 0) {
+    LK_CUDA(cudaMemsetAsync(a0.part_cnt, 0, n_cnt0 * sizeof(int), st));  // lists are read up to their count
+    if ((rc = launch_search_umma(a0, ix->sm_count, st)) != LK_OK) return rc;
+    rc = launch_merge_i32(a0.part_scores, a0.part_idx, a0.part_cnt, b, a0.n_lists, merge_len, a0.ksel, k, 0, d_s,
+                          d_i, st);
+    if (rc != LK_OK) return rc;
+    a.seed = d_s;  // read at the start of the main kernel's segments, overwritten by the final merge
+  }
+  if (counted) {
+    LK_CUDA(cudaMemsetAsync(a.part_cnt, 0, n_cnt * sizeof(int), st));
+  } else {
+    LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
+    LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
+  }
   if (which == LK_KERNEL_UMMA) rc = launch_search_umma(a, ix->sm_count, st);
   else rc = launch_search_simt(a, ix->sm_count, st);
   if (rc != LK_OK) return rc;
@@ -475,16 +514,11 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     }
   }
 
-  // 4. merge the per-CTA lists
-  float* d_s = out_scores;
-  int64_t* d_i = out_idx;
-  if (out_mem == LK_HOST) {
-    if ((rc = ix->out_s.ensure((size_t)b * k * sizeof(float))) != LK_OK) return rc;
-    if ((rc = ix->out_i.ensure((size_t)b * k * sizeof(int64_t))) != LK_OK) return rc;
-    d_s = ix->out_s.as<float>();
-    d_i = ix->out_i.as<int64_t>();
-  }
-  rc = launch_merge_i32(a.part_scores, a.part_idx, b, a.n_lists, a.ksel, k, idx_base, d_s, d_i, st);
+  // 4. merge the per-CTA lists.  Sorted selectors leave their best k in the first k slots; the
+  // append-buffer selector (ksel > kMaxK) leaves an unordered superset of its best k anywhere
+  // in the slot
+  rc = launch_merge_i32(a.part_scores, a.part_idx, a.part_cnt, b, a.n_lists, merge_len, a.ksel, k, idx_base, d_s, d_i,
+                        st);
   if (rc != LK_OK) return rc;
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[3], st));
 

@@ -104,7 +104,9 @@ struct SearchArgs {
   int n_lists;             // partial lists per query (stride of the partial arrays)
   float* part_scores;      // [n_queries, n_lists, ksel]
   int32_t* part_idx;       // [n_queries, n_lists, ksel]
+  int* part_cnt;           // [n_queries, n_lists] fill counts (append-buffer selector), or null
   int* err_flag;           // device int, set non-zero by a kernel that timed out
+  const float* seed;       // tcgen05 kernel, k > 32: [n_queries, k] scores of a sample search, or null
   float* debug_tile;       // optional [128 x 128] dump of unit 0's raw accumulator (bring-up aid)
 };
 
@@ -112,11 +114,14 @@ int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
 int launch_search_simt(const SearchArgs& a, int sm_count, cudaStream_t st);
 int umma_supported(const TileGeom& g, int k);
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
+// rows of the corpus prefix whose top-k seeds the selection thresholds (0 = do not seed)
+int64_t umma_seed_rows(const SearchArgs& a, int sm_count);
 int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st);
 
 // merge [b, n_lists, list_len] candidates -> [b, k]; idx type int32 (+base) or int64
-int launch_merge_i32(const float* ps, const int32_t* pi, int64_t b, int n_lists, int list_len, int k,
-                     int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st);
+// pc: optional [b, n_lists] fill counts of the lists (entries past the count are not read)
+int launch_merge_i32(const float* ps, const int32_t* pi, const int* pc, int64_t b, int n_lists, int list_len,
+                     int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st);
 int launch_merge_i64(const float* ps, const int64_t* pi, int64_t b, int n_lists, int list_len, int k,
                      float* out_s, int64_t* out_i, cudaStream_t st);
 

@@ -73,12 +73,16 @@ struct UmmaParams {
   int n_stages;
   int n_lists;
   int64_t block_bytes;
-  int ksel;              // entries per partial list (KSEL, or k for the heap selector)
+  int ksel;              // entries per partial list slot (KSEL, or kBufCap for the buffer selector)
+  int k;                 // requested k
   float* part_scores;    // [n_queries, n_lists, ksel]
   int32_t* part_idx;
+  int* part_cnt;         // [n_queries, n_lists] entries left in each list slot (buffer selector), or null
   int* err_flag;
+  const float* seed;     // [n_queries, k] best-first scores over a corpus sample, or null
   float* debug_tile;     // [128 queries][128 rows] raw dot products of unit 0, or null
   uint32_t lbo, sbo;
+  int dbg;
 };
 
 __host__ __device__ inline int64_t unit_begin(int64_t c, int64_t total, int64_t grid) {
@@ -161,6 +165,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     int seg = 0;
     int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
     bool ok = true;
+    // one query tile = every row block is read exactly once: stream it evict-first so that the
+    // query tile and the partial lists stay in L2; with several query tiles the row blocks are
+    // shared through L2 by the CTAs working on the same corpus offset, so they keep the default
+    const bool stream_once = p.total_units == p.nblk && !(p.dbg & 2);
+    const uint64_t stream_policy = ptx::policy_evict_first();
     for (int64_t u = u0; u < u1 && ok; ++u) {
       const unsigned char* q_src = p.q_tiles + (int64_t)qt * p.block_bytes;
       if (QRES && (u == u0 || b == 0)) {
@@ -188,9 +197,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           const uint32_t dst = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
           ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
 #pragma unroll
-          for (int h = 0; h < kUnitBlocks; ++h)  // rows 0-127 and 128-255 of the N=256 operand
-            ptx::bulk_g2s(dst + h * kKBlockBytes, e_src + h * p.block_bytes + (int64_t)kb * kKBlockBytes,
-                          kKBlockBytes, full_bar(st.idx));
+          for (int h = 0; h < kUnitBlocks; ++h) {  // rows 0-127 and 128-255 of the N=256 operand
+            const unsigned char* src = e_src + h * p.block_bytes + (int64_t)kb * kKBlockBytes;
+            if (stream_once) ptx::bulk_g2s_hint(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx), stream_policy);
+            else ptx::bulk_g2s(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx));
+          }
           if (!QRES)
             ptx::bulk_g2s(dst + kUnitBlocks * kKBlockBytes, q_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
                           full_bar(st.idx));
@@ -269,8 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     int slot = 0;
     int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
     typename SelectorFor<KSEL>::type top;
+    const uint64_t keep_policy = ptx::policy_evict_last();
     float thr = INFINITY;
     float q_sd = 0.f;
+    int* cnt_out = nullptr;
     bool seg_start = true;
     if (u0 < u1) {
       const float* sp = p.side + (int64_t)b * kUnitCols + ch * kColsPerWarp;
@@ -286,7 +299,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         const int64_t c_first = cta_of_unit((int64_t)qt * p.nblk, p.total_units, G);
         const int list = (int)(c - c_first) * kColSplit + ch;
         const int64_t o = q_ok ? (q * p.n_lists + list) * p.ksel : 0;
-        top.begin(p.part_scores + o, p.part_idx + o, q_ok, p.ksel);
+        // seeded threshold: the k-th best score over a sample of the corpus (found by an earlier
+        // launch over a prefix of the rows) bounds the final k-th best from below; taken a hair
+        // lower so that the sample's own k-th row passes again, in this kernel's score space
+        float floor = -INFINITY;
+        if (p.seed != nullptr && q_ok) {
+          float sd = p.seed[q * p.k + (p.k - 1)];
+          if (sd > -INFINITY) {
+            if (METRIC == LK_COSINE) sd = sd / q_sd;  // q_sd = 1/|q| > 0
+            const float mag = METRIC == LK_COSINE ? fabsf(sd) : fabsf(sd) + q_sd;
+            floor = sd - fmaxf(4e-6f * mag, 1e-37f);
+          }
+        }
+        top.begin(p.part_scores + o, p.part_idx + o, q_ok, p.k, floor);
+        cnt_out = (q_ok && p.part_cnt != nullptr) ? p.part_cnt + (q * p.n_lists + list) : nullptr;
         thr = top.threshold();
         seg_start = false;
       }
@@ -332,10 +358,34 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           if (METRIC == LK_COSINE) return dot * e_sd;            // x 1/|e|; x 1/|q| at flush
           return fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
         };
-        float m = -INFINITY;
+        float mg[4];  // running max per group of 8 columns (NaN never wins)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m = fmaxf(m, score(__uint_as_float(r[j]), sdc[j]));  // NaN never wins
-        if (__any_sync(0xffffffffu, m > thr)) {
+        for (int g = 0; g < 4; ++g) {
+          mg[g] = -INFINITY;
+#pragma unroll
+          for (int j = 8 * g; j < 8 * g + 8; ++j) mg[g] = fmaxf(mg[g], score(__uint_as_float(r[j]), sdc[j]));
+        }
+        const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
+        if constexpr (SelectorFor<KSEL>::type::kAppend) {
+          // k > 10: every lane appends its own hits (predicated, no divergence, no TMEM re-read),
+          // only in the 8-column groups where some lane has one; then the warp compacts the
+          // buffers that are about to run out of room for a chunk.
+          if (__any_sync(0xffffffffu, m > thr)) {
+            top.note_max(m);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (__any_sync(0xffffffffu, mg[g] > thr)) {
+#pragma unroll
+                for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                  const float sc = score(__uint_as_float(r[j]), sdc[j]);
+                  if (sc > thr) top.append(sc, row0 + chunk * 32 + j, keep_policy);  // thr fixed between compactions
+                }
+              }
+            }
+            top.compact(kBufCap - 32, lane, keep_policy);  // room for one more chunk, or shrink now
+            thr = top.threshold();
+          }
+        } else if (__any_sync(0xffffffffu, m > thr)) {
           unsigned pend = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -358,6 +408,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(acc.idx));
       acc.advance(kAccStages);
+      if constexpr (SelectorFor<KSEL>::type::kAppend) {
+        // routine compactions run here, after the accumulator went back to the MMA warp, a few
+        // lanes per unit, so they overlap the next unit instead of stalling the pipeline
+        top.compact(kBufCap - 64, lane, keep_policy, 4);
+        thr = top.threshold();
+      }
       slot ^= 1;
 #pragma unroll
       for (int j = 0; j < kColsPerWarp / 32; ++j) my_side[slot * kColsPerWarp + lane + 32 * j] = ns[j];
@@ -365,7 +421,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 
       const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
       if (seg_end) {
-        top.finish(q_sd, METRIC == LK_COSINE, p.ksel);  // cosine: x 1/|q| once per kept entry
+        top.finish(q_sd, METRIC == LK_COSINE, p.k, lane);  // cosine: x 1/|q| once per kept entry
+        if constexpr (SelectorFor<KSEL>::type::kAppend)
+          if (cnt_out != nullptr) *cnt_out = top.cnt;
         seg_start = true;
       }
       b = nb;
@@ -390,7 +448,7 @@ inline int n_stages_for(const TileGeom& g) {
   int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage;
   return s > kMaxStages ? kMaxStages : s;
 }
-inline int ksel_for(int k) { return k <= 10 ? 10 : (k <= 32 ? 32 : k); }  // > 32: heap of exactly k
+inline int ksel_for(int k) { return k <= 10 ? 10 : kBufCap; }  // sorted register list / append buffer
 
 }  // namespace
 
@@ -413,6 +471,22 @@ int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
   return LK_OK;
 }
 
+// Threshold seeding (k > 32, up to 1024 queries): every (CTA, column half) list starts cold, and
+// with few query tiles each list sees only 1/(2 x CTAs) of the rows, so most of what it
+// appends is far from the global top-k.  Searching a short prefix of the corpus first (one unit
+// = 256 rows per CTA: every list takes at most 128 entries and never compacts) gives every list
+// a threshold that only k * rows / prefix_rows rows of the whole corpus beat.
+int64_t umma_seed_rows(const SearchArgs& a, int sm_count) {
+  if (ksel_for(a.k) != kBufCap || a.n_queries < 8 || a.n_queries > 1024) return 0;
+  if (const char* e = getenv("LK_SEED"))  // bring-up override
+    if (!atoi(e)) return 0;
+  const int64_t units = (a.n_rows + kUnitCols - 1) / kUnitCols;
+  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
+  const int64_t s_units = (sm_count + nqt - 1) / nqt;  // one unit per CTA: no list can fill up
+  if (units < 16 * s_units) return 0;
+  return s_units * kUnitCols;
+}
+
 int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   if (a.n_queries <= 0 || a.n_rows <= 0) return LK_OK;
   if (!umma_supported(a.g, a.k)) {
@@ -433,11 +507,15 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.n_stages = n_stages_for(a.g);
   p.n_lists = a.n_lists;
   p.ksel = a.ksel;
+  p.k = a.k;
   p.block_bytes = a.g.block_bytes();
   p.part_scores = a.part_scores;
   p.part_idx = a.part_idx;
+  p.part_cnt = a.part_cnt;
   p.err_flag = a.err_flag;
+  p.seed = a.seed;
   p.debug_tile = a.debug_tile;
+  p.dbg = getenv("LK_DBG") ? atoi(getenv("LK_DBG")) : 0;
   p.lbo = kLbo;
   p.sbo = kSbo;
   if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
@@ -465,10 +543,8 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   } while (0)
   if (ksel == 10) {
     if (qres) LK_UMMA_M(10, true); else LK_UMMA_M(10, false);
-  } else if (ksel == 32) {
-    if (qres) LK_UMMA_M(32, true); else LK_UMMA_M(32, false);
   } else {
-    if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);
+    if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);  // KSEL 0 = BufSelector
   }
 #undef LK_UMMA_M
 #undef LK_UMMA

@@ -12,6 +12,7 @@
 #pragma once
 
 #include "lk_common.cuh"
+#include "lk_ptx.cuh"
 
 namespace lk {
 
@@ -116,22 +117,25 @@ struct RegTopK {
 };
 
 // Selector interfaces used by the tcgen05 epilogue (one thread = one query):
-//   begin(list_scores, list_idx, valid)  start a (query, partial-list) segment
+//   begin(list_scores, list_idx, valid, k, floor)  start a (query, partial-list) segment
 //   threshold() / insert(score, id)      running top-k (insert requires score > threshold())
 //   finish(scale)                        leave the list in list_scores / list_idx
+// RegSelector keeps a sorted list in registers (k <= 32); BufSelector (kAppend) appends to a
+// buffer in the list slot and compacts it cooperatively (k <= 128).
 template <int K>
 struct RegSelector {
+  static constexpr bool kAppend = false;
   RegTopK<K> top;
   float* out_s;
   int32_t* out_i;
   bool valid;
-  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int /*k*/) {
+  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int /*k*/, float /*floor*/) {
     out_s = s; out_i = ix; valid = v;
     top.init();
   }
   __device__ __forceinline__ float threshold() const { return top.threshold(); }
   __device__ __forceinline__ void insert(float v, int32_t id) { top.insert(v, id); }
-  __device__ __forceinline__ void finish(float scale, bool apply_scale, int /*k*/) {
+  __device__ __forceinline__ void finish(float scale, bool apply_scale, int /*k*/, int /*lane*/) {
     if (!valid) return;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
@@ -141,59 +145,201 @@ struct RegSelector {
   }
 };
 
-// k up to 128: a binary heap (root = worst kept entry) living directly in the thread's
-// partial-list slot in global memory (L2-resident; touched only on the rare insert).
-struct HeapSelector {
-  float* hs;
-  int32_t* hi;
-  float thr;
+// k up to 128: an APPEND BUFFER of kBufCap entries living in the thread's partial-list slot
+// in global memory (L2-resident: evict-last stores).  A candidate that beats the current
+// threshold is appended with two fire-and-forget stores (no ordering kept, no dependent
+// loads).  When a lane's buffer is nearly full the WARP shrinks it cooperatively: the 256
+// entries sit in registers (8 per lane, coalesced loads, the next buffer's loads already in
+// flight), a pivot t with k <= #{score >= t} <= k + kBufSlack is found by counting against 7
+// candidates per pass (they split the known score range [threshold, running max] evenly in
+// order-preserving key space, so every pass narrows the range 8x; three packed warp
+// reductions per pass), then a stable rewrite keeps the entries at or above the pivot.
+// Entries are always in ascending row order (rows arrive ascending, the rewrite is stable), so
+// when the pivot is the exact k-th score the surplus entries equal to it are dropped from the
+// back: (score desc, index asc) holds without storing an order.  Each compaction multiplies the
+// rows seen by ~(1 + room / k), so a list needs only O(log(rows / k)) of them.
+constexpr int kBufCap = 256;
+constexpr int kBufSlack = 24;
+constexpr int kBufPer = kBufCap / 32;
+
+__device__ __forceinline__ uint32_t order_key(float f) {  // monotone float -> uint32
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// entries e = j * 32 + lane of one buffer -> registers (keys of missing entries are 0: below
+// every real key)
+__device__ __forceinline__ void buffer_load(const float* bs, const int32_t* bi, int n, int lane,
+                                            uint32_t (&key)[kBufPer], int32_t (&id)[kBufPer]) {
+#pragma unroll
+  for (int j = 0; j < kBufPer; ++j) {
+    const int e = j * 32 + lane;
+    key[j] = 0u;
+    id[j] = -1;
+    if (e < n) {
+      key[j] = order_key(__ldcg(bs + e));
+      id[j] = __ldcg(bi + e);
+    }
+  }
+}
+
+// Whole warp, one buffer held in registers: every key is in [lo, hi].  Rewrites the survivors
+// in place (stable), returns the pivot key; *kept = survivors.
+__device__ __forceinline__ uint32_t buffer_shrink(float* bs, int32_t* bi, int n, int k, uint32_t lo, uint32_t hi,
+                                                  int lane, uint64_t keep_policy, const uint32_t (&key)[kBufPer],
+                                                  const int32_t (&id)[kBufPer], int* kept) {
+  uint32_t t = lo;
+  int c_t = n;  // #{key >= t}
+#pragma unroll 1
+  for (int pass = 0; pass < 16 && c_t > k + kBufSlack && hi > t; ++pass) {
+    const uint32_t step = (hi - t) / 8u + 1u;
+    int c[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) c[j] = 0;
+#pragma unroll
+    for (int i = 0; i < kBufPer; ++i)
+#pragma unroll
+      for (int j = 0; j < 7; ++j) c[j] += key[i] >= t + step * (uint32_t)(j + 1) ? 1 : 0;
+    // per-lane counts are <= 8 and warp totals <= 256: three 10-bit fields per reduction
+    const unsigned w0 = __reduce_add_sync(0xffffffffu, (unsigned)(c[0] | (c[1] << 10) | (c[2] << 20)));
+    const unsigned w1 = __reduce_add_sync(0xffffffffu, (unsigned)(c[3] | (c[4] << 10) | (c[5] << 20)));
+    const unsigned w2 = __reduce_add_sync(0xffffffffu, (unsigned)c[6]);
+    const int tot[7] = {(int)(w0 & 1023u), (int)((w0 >> 10) & 1023u), (int)(w0 >> 20),
+                        (int)(w1 & 1023u), (int)((w1 >> 10) & 1023u), (int)(w1 >> 20), (int)w2};
+    uint32_t nt = t, nhi = t + step - 1u;
+    int nc = c_t;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (tot[j] >= k) {  // counts fall as j grows
+        nt = t + step * (uint32_t)(j + 1);
+        nc = tot[j];
+        nhi = j < 6 ? t + step * (uint32_t)(j + 2) - 1u : hi;
+      }
+    t = nt;
+    c_t = nc;
+    hi = nhi < hi ? nhi : hi;
+  }
+  // ties: when more than the slack survive, t is the exact k-th key (hi == t) and only the
+  // earliest k - #{key > t} of the entries equal to it are needed
+  int need_eq = 1 << 30;
+  if (c_t > k + kBufSlack) {
+    int cgt = 0;
+#pragma unroll
+    for (int i = 0; i < kBufPer; ++i) cgt += key[i] > t ? 1 : 0;
+    need_eq = k - (int)__reduce_add_sync(0xffffffffu, (unsigned)cgt);
+    if (need_eq < 0) need_eq = 0;
+  }
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int base = 0, eq_seen = 0;
+#pragma unroll
+  for (int j = 0; j < kBufPer; ++j) {  // position order: e = j * 32 + lane
+    const bool eq = key[j] == t;
+    const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+    const bool keep = key[j] > t || (eq && eq_seen + __popc(eqm & lt_mask) < need_eq);
+    eq_seen += __popc(eqm);
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = base + __popc(km & lt_mask);
+      ptx::st_hint(bs + pos, order_key_inv(key[j]), keep_policy);
+      ptx::st_hint(bi + pos, id[j], keep_policy);
+    }
+    base += __popc(km);
+  }
+  *kept = base;
+  return t;
+}
+
+struct BufSelector {
+  static constexpr bool kAppend = true;
+  float* bs;
+  int32_t* bi;
+  float thr;    // entries must beat this; every buffered entry scores >= thr
+  float vmax;   // upper bound of every buffered score
+  int cnt;
   bool valid;
   int k;
-  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int kk) {
-    hs = s; hi = ix; valid = v; k = kk;
-    thr = v ? -INFINITY : INFINITY;  // lanes without a query never insert
-    if (v)
-      for (int j = 0; j < kk; ++j) {
-        hs[j] = -INFINITY;
-        hi[j] = 0x7fffffff;
-      }
+  // floor: a score known to be BELOW the query's final k-th best (-inf when unknown)
+  __device__ __forceinline__ void begin(float* s, int32_t* ix, bool v, int kk, float floor) {
+    bs = s; bi = ix; valid = v; k = kk; cnt = 0;
+    vmax = -INFINITY;
+    thr = v ? floor : INFINITY;  // lanes without a query never append
   }
   __device__ __forceinline__ float threshold() const { return thr; }
-  // precondition: v > thr (rows arrive in ascending index order)
-  __device__ __forceinline__ void insert(float v, int32_t id) {
-    int i = 0;
-    for (;;) {
-      const int l = 2 * i + 1;
-      if (l >= k) break;
-      int c = l;
-      float sc = hs[l];
-      int32_t ic = hi[l];
-      if (l + 1 < k) {  // descend towards the WORSE child: lower score, higher index on ties
-        const float sr = hs[l + 1];
-        const int32_t ir = hi[l + 1];
-        if (sr < sc || (sr == sc && ir > ic)) {
-          c = l + 1; sc = sr; ic = ir;
-        }
+  __device__ __forceinline__ void note_max(float m) { vmax = fmaxf(vmax, m); }
+  // precondition: v > thr (and note_max has seen v).  The stores carry an evict-last hint: a
+  // list is touched every few microseconds while the corpus streams through L2, and a partially
+  // written sector that gets evicted in between costs a DRAM fill plus a write-back per append.
+  __device__ __forceinline__ void append(float v, int32_t id, uint64_t keep_policy) {
+    ptx::st_hint(bs + cnt, v, keep_policy);
+    ptx::st_hint(bi + cnt, id, keep_policy);
+    ++cnt;
+  }
+  // Whole warp: shrink the buffers of (at most `budget`) lanes holding more than `limit` entries,
+  // one after the other, the next buffer's loads in flight while the current one is processed.
+  __device__ __forceinline__ void compact(int limit, int lane, uint64_t keep_policy, int budget = 32) {
+    unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
+    if (!todo) return;
+    __syncwarp();  // the appends of every lane are visible to the warp
+    auto ptr_s = [&](int src) {
+      return reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bs), src));
+    };
+    auto ptr_i = [&](int src) {
+      return reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bi), src));
+    };
+    uint32_t key[kBufPer], nkey[kBufPer];
+    int32_t id[kBufPer], nid[kBufPer];
+    int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    float* ps = ptr_s(src);
+    int32_t* pi = ptr_i(src);
+    int n = __shfl_sync(0xffffffffu, cnt, src);
+    buffer_load(ps, pi, n, lane, key, id);
+    while (src >= 0) {
+      int nsrc = -1, nn = 0;
+      float* nps = nullptr;
+      int32_t* npi = nullptr;
+      if (todo && --budget > 0) {
+        nsrc = __ffs(todo) - 1;
+        todo &= todo - 1;
+        nps = ptr_s(nsrc);
+        npi = ptr_i(nsrc);
+        nn = __shfl_sync(0xffffffffu, cnt, nsrc);
+        buffer_load(nps, npi, nn, lane, nkey, nid);
       }
-      if (sc < v || (sc == v && ic > id)) {  // child is worse than the new entry: move it up
-        hs[i] = sc;
-        hi[i] = ic;
-        i = c;
-      } else {
-        break;
+      const float t_old = __shfl_sync(0xffffffffu, thr, src);
+      const uint32_t lo = t_old > -INFINITY ? order_key(t_old) : 0x007fffffu;
+      const uint32_t hi = order_key(__shfl_sync(0xffffffffu, vmax, src));
+      const int kk = __shfl_sync(0xffffffffu, k, src);
+      int kept;
+      const uint32_t t = buffer_shrink(ps, pi, n, kk, lo, hi, lane, keep_policy, key, id, &kept);
+      if (lane == src) {
+        cnt = kept;
+        thr = order_key_inv(t);
+      }
+      src = nsrc;
+      ps = nps;
+      pi = npi;
+      n = nn;
+#pragma unroll
+      for (int j = 0; j < kBufPer; ++j) {
+        key[j] = nkey[j];
+        id[j] = nid[j];
       }
     }
-    hs[i] = v;
-    hi[i] = id;
-    thr = hs[0];
+    __syncwarp();
   }
-  __device__ __forceinline__ void finish(float scale, bool apply_scale, int kk) {
-    if (!valid || !apply_scale) return;
-    for (int j = 0; j < kk; ++j) hs[j] *= scale;
+  // Leaves the best entries seen (at least min(k, seen) of them, unordered, at most kBufCap) in
+  // slots [0, cnt); the merge kernel does the final selection.
+  __device__ __forceinline__ void finish(float scale, bool apply_scale, int /*kk*/, int /*lane*/) {
+    if (valid && apply_scale)
+      for (int j = 0; j < cnt; ++j) bs[j] = __ldcg(bs + j) * scale;
   }
 };
 
 template <int KSEL> struct SelectorFor { using type = RegSelector<KSEL>; };
-template <> struct SelectorFor<0> { using type = HeapSelector; };
+template <> struct SelectorFor<0> { using type = BufSelector; };
 
 }  // namespace lk

@@ -125,11 +125,16 @@ SHAPES = [
     (3000, 200, 768, 30),
     (40000, 1, 384, 10),
     (2500, 1500, 64, 10),
-    # k > 32: per-thread heap selector
+    # k > 32: append-buffer selector (lists that never fill, fill once, compact many times)
     (3000, 40, 768, 100),
     (20000, 150, 384, 128),
     (500, 7, 64, 64),
     (300, 3, 32, 100),
+    (200000, 8, 64, 100),
+    (60000, 2500, 64, 100),
+    (150000, 130, 128, 33),
+    (400000, 40, 64, 100),   # large enough for threshold seeding from a corpus-prefix search
+    (330000, 300, 32, 128),
 ]
 
 
@@ -138,7 +143,7 @@ SHAPES = [
 def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
     """tcgen05 kernel over ragged shapes: partial row blocks, partial query tiles, several
     query tiles per CTA range, K padding (dim 32/100), streamed-Q (dim 768), k in both
-    register-list sizes and in the heap selector (k > 32)."""
+    register-list sizes and in the append-buffer selector (k > 32)."""
     monkeypatch.setenv("LK_FORCE_KERNEL", "umma")
     rng = np.random.default_rng(n * 7 + b)
     emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
@@ -167,8 +172,9 @@ def test_simt_kernel_matches_oracle(lrb, n, b, dim, k, precision, metric, monkey
     _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
 
 
+@pytest.mark.parametrize("k", [6, 40, 128])
 @pytest.mark.parametrize("kernel", ["simt", "umma"])
-def test_ties_resolve_to_the_lowest_index(lrb, kernel, monkeypatch):
+def test_ties_resolve_to_the_lowest_index(lrb, kernel, k, monkeypatch):
     """Duplicate rows give exactly equal scores; the engine's order is (score desc, index asc)
     whatever the partitioning.  (torch.topk's tie order is unspecified.)"""
     monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
@@ -176,11 +182,14 @@ def test_ties_resolve_to_the_lowest_index(lrb, kernel, monkeypatch):
     base = oracle.bf16_round(torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32)))
     emb = torch.cat([base, base, base])  # rows j, j+300, j+600 identical
     r = lrb.BruteForceRetriever(emb, [""] * 900, None, metric="euclidean")
-    d, i = r.search(base[:20], 6)
+    d, i = r.search(base[:20], k)
     for row in range(20):
         assert i[row, :3].tolist() == [row, row + 300, row + 600]
         assert d[row, 0] == d[row, 1] == d[row, 2]
-    d_ref, i_ref = _oracle(emb, base[:20], 6, "euclidean")
+        for t in range(0, k - k % 3, 3):  # every triple of equal scores is in ascending row order
+            assert d[row, t] == d[row, t + 1] == d[row, t + 2]
+            assert i[row, t] + 300 == i[row, t + 1] and i[row, t] + 600 == i[row, t + 2]
+    d_ref, i_ref = _oracle(emb, base[:20], k, "euclidean")
     _assert_topk(d_ref, i_ref, d, i, l2=(emb, base[:20]))
 
 
@@ -389,7 +398,9 @@ def test_latent_pipeline_config2_shape(lrb):
 # ---------------------------------------------------------------------------------------
 def test_merge_kernel_matches_oracle(lrb):
     rng = np.random.default_rng(12)
-    for b, lists, ln, k in [(1, 8, 10, 10), (33, 3, 100, 100), (257, 8, 10, 7), (5, 2, 128, 128)]:
+    # the last cases go through the selection merge (few queries, >= 2048 candidates each)
+    for b, lists, ln, k in [(1, 8, 10, 10), (33, 3, 100, 100), (257, 8, 10, 7), (5, 2, 128, 128),
+                            (1, 296, 10, 10), (3, 296, 256, 100), (64, 40, 64, 33), (2, 300, 256, 128)]:
         cd = rng.standard_normal((b, lists, ln)).astype(np.float32)
         ci = rng.permutation(b * lists * ln).reshape(b, lists, ln).astype(np.int64)
         ci[:, -1, -2:] = -1  # padding
@@ -400,6 +411,19 @@ def test_merge_kernel_matches_oracle(lrb):
         np.testing.assert_array_equal(d, d_ref)
         dg, ig = lrb.merge_topk(torch.from_numpy(cd).cuda(), torch.from_numpy(ci).cuda(), k)
         np.testing.assert_array_equal(ig.cpu().numpy(), i_ref)
+
+
+def test_merge_selection_with_massive_ties(lrb):
+    """More tied candidates at the k-th score than the selection merge gathers: lowest ids win."""
+    rng = np.random.default_rng(13)
+    cd = rng.standard_normal((2, 30, 100)).astype(np.float32)
+    ci = rng.permutation(2 * 30 * 100).reshape(2, 30, 100).astype(np.int64)
+    cd[0, :, 10:40] = 2.5   # 900 candidates share the score around rank 13..912
+    cd[1, :, :] = -3.0      # every candidate ties
+    d, i = lrb.merge_topk(cd, ci, 100)
+    d_ref, i_ref = oracle.merge_topk(cd, ci, 100)
+    np.testing.assert_array_equal(i, i_ref)
+    np.testing.assert_array_equal(d, d_ref)
 
 
 @pytest.mark.parametrize("world", [1, 2, 8])
