@@ -421,7 +421,7 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[0], st));
 
   // 1. queries -> tiles (+ side values), same geometry and rounding as the corpus
-  const int64_t b_pad = round_up64(b, kBlockRows);
+  const int64_t b_pad = round_up64(b, 2 * kBlockRows);  // whole PAIRS of query tiles (CTA-pair kernel)
   const size_t qt_bytes = (size_t)(b_pad / kBlockRows) * ix->g.block_bytes();
   if ((rc = ix->q_tiles.ensure(qt_bytes)) != LK_OK) return rc;
   if ((rc = ix->q_side.ensure((size_t)b_pad * sizeof(float))) != LK_OK) return rc;

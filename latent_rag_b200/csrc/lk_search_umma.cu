@@ -50,7 +50,8 @@ constexpr int kKBlockElems = kRowBytes / 2;              // 64 bf16 per row per 
 constexpr int kKBlockBytes = kSlabBytes;                 // 16384
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kHeaderBytes = 256 + kEpiWarps * 2 * kColsPerWarp * 4;  // barriers + side rings
+constexpr int kBarBytes = 512;                           // barriers, TMEM pointer, abort flag
+constexpr int kHeaderBytes = kBarBytes + kEpiWarps * 2 * kColsPerWarp * 4;  // + side rings
 constexpr int kAlignSlack = 1024;                        // stages must be 1024-aligned (swizzle atom)
 constexpr uint32_t kLbo = 16;                            // unused by swizzled K-major layouts
 constexpr uint32_t kSbo = 8 * kRowBytes;                 // 1024: next 8-row group
@@ -58,7 +59,8 @@ constexpr uint32_t kUmmaKBytes = 32;                     // 16 bf16 = one MMA's 
 
 enum UmmaErr {
   kErrProdEmpty = 101, kErrProdQEmpty = 102, kErrMmaFull = 103, kErrMmaTmemEmpty = 104,
-  kErrMmaQFull = 105, kErrEpiTmemFull = 106
+  kErrMmaQFull = 105, kErrEpiTmemFull = 106, kErrMmaPeerFull = 107, kErrMmaPeerQFull = 108,
+  kErrRelayFull = 109, kErrRelayQFull = 110
 };
 
 struct UmmaParams {
@@ -104,51 +106,71 @@ struct Ring {
   }
 };
 
-template <int KSEL, int METRIC, bool QRES>
+// CG = 1: one CTA per scheduling group (above).  CG = 2: a CTA PAIR per group
+// (tcgen05 cta_group::2): the pair works on two query tiles at once (M = 256: the leader's tile
+// -> the leader's TMEM, the peer's tile -> the peer's), each CTA loads only ITS half of the 256
+// corpus rows of a unit (16 KB per K block instead of 32: half the L2 -> SM traffic and
+// shared-memory operand reads per FLOP, twice the pipeline depth in the same shared memory).
+// Only the leader issues MMAs; its commits are multicast to the barriers of both CTAs; the
+// peer's warp 1 relays "my stage / query tile has landed" to the leader, and the peer's
+// epilogue warps release the accumulator on the leader's barrier.
+template <int KSEL, int METRIC, bool QRES, int CG>
 __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // barrier slots: full[8] empty[8] tfull[4] tempty[4] qfull qempty
+  // barrier slots: full[8] empty[8] peer_full[8] tfull[2] tempty[2] qfull qempty peer_qfull
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + kAccStages + s); };
-  const uint32_t qfull_bar = bar0 + 8u * (2 * kMaxStages + 2 * kAccStages);
+  auto pfull_bar = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * kMaxStages + kAccStages + s); };
+  const uint32_t qfull_bar = bar0 + 8u * (3 * kMaxStages + 2 * kAccStages);
   const uint32_t qempty_bar = qfull_bar + 8u;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + 240);
-  volatile int* abort_s = reinterpret_cast<volatile int*>(smem + 244);
-  float* side_ring = reinterpret_cast<float*>(smem + 256);
+  const uint32_t pqfull_bar = qfull_bar + 16u;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + kBarBytes - 16);
+  volatile int* abort_s = reinterpret_cast<volatile int*>(smem + kBarBytes - 12);
+  float* side_ring = reinterpret_cast<float*>(smem + kBarBytes);
   unsigned char* q_sm = smem + kHeaderBytes;
   q_sm += (1024u - (ptx::smem_u32(q_sm) & 1023u)) & 1023u;  // swizzle atoms are 1024-byte aligned
   unsigned char* stage_sm = q_sm + (QRES ? p.nkb * kKBlockBytes : 0);
-  constexpr int kStageBytes = (QRES ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
+  constexpr int kSlabsPerStage = kUnitBlocks / CG;  // corpus row blocks this CTA loads per K block
+  constexpr int kStageBytes = (QRES ? kSlabsPerStage : kSlabsPerStage + 1) * kKBlockBytes;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
-  const int64_t G = gridDim.x, c = blockIdx.x;
+  const int rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;  // 0 = leader
+  const int64_t G = gridDim.x / CG, c = blockIdx.x / CG;        // scheduling groups, this CTA's group
   const int64_t u0 = unit_begin(c, p.total_units, G), u1 = unit_begin(c + 1, p.total_units, G);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(pfull_bar(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), kEpiWarps);
+      ptx::mbar_init(tempty_bar(s), kEpiWarps * CG);  // the leader's collects both CTAs' epilogue warps
     }
     ptx::mbar_init(qfull_bar, 1);
     ptx::mbar_init(qempty_bar, 1);
+    ptx::mbar_init(pqfull_bar, 1);
     *abort_s = 0;
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc2(ptx::smem_u32(tmem_ptr_s), kTmemCols);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_ptr_s), kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();  // the peer's barriers exist before anyone arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
@@ -163,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     // registers); one elected lane issues the copies.
     Ring st;
     int seg = 0;
-    int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
+    int qt = (int)(u0 / p.nblk) * CG + rank, b = (int)(u0 % p.nblk);
     bool ok = true;
     // one query tile = every row block is read exactly once: stream it evict-first so that the
     // query tile and the partial lists stay in L2; with several query tiles the row blocks are
@@ -197,13 +219,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           const uint32_t dst = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
           ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
 #pragma unroll
-          for (int h = 0; h < kUnitBlocks; ++h) {  // rows 0-127 and 128-255 of the N=256 operand
-            const unsigned char* src = e_src + h * p.block_bytes + (int64_t)kb * kKBlockBytes;
+          for (int h = 0; h < kSlabsPerStage; ++h) {  // rows 0-127 and 128-255 of the N=256 operand (CG=2: this CTA's half)
+            const unsigned char* src = e_src + (h + rank * kSlabsPerStage) * p.block_bytes + (int64_t)kb * kKBlockBytes;
             if (stream_once) ptx::bulk_g2s_hint(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx), stream_policy);
             else ptx::bulk_g2s(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx));
           }
           if (!QRES)
-            ptx::bulk_g2s(dst + kUnitBlocks * kKBlockBytes, q_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
+            ptx::bulk_g2s(dst + kSlabsPerStage * kKBlockBytes, q_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
                           full_bar(st.idx));
         }
         __syncwarp();
@@ -211,14 +233,44 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       }
       if (++b == p.nblk) {
         b = 0;
-        ++qt;
+        qt += CG;
       }
+    }
+  } else if (warp == 1 && CG == 2 && rank != 0) {
+    // ===================== peer relay =====================
+    // Tells the leader's MMA warp that THIS CTA's copies have landed (a bulk copy can only
+    // complete on a barrier of its own CTA).
+    Ring st;
+    int seg = 0;
+    int b = (int)(u0 % p.nblk);
+    bool ok = true;
+    for (int64_t u = u0; u < u1 && ok; ++u) {
+      if (QRES && (u == u0 || b == 0)) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1)))) {
+          fail(kErrRelayQFull);
+          break;
+        }
+        if (ptx::elect_one()) ptx::mbar_arrive_remote(pqfull_bar, 0);
+        __syncwarp();
+        ++seg;
+      }
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        if (!__all_sync(0xffffffffu, ptx::mbar_wait(full_bar(st.idx), st.phase))) {
+          fail(kErrRelayFull);
+          ok = false;
+          break;
+        }
+        if (ptx::elect_one()) ptx::mbar_arrive_remote(pfull_bar(st.idx), 0);
+        __syncwarp();
+        st.advance(p.n_stages);
+      }
+      if (++b == p.nblk) b = 0;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // Warp-uniform loop; one elected lane issues the 4 tcgen05.mma of a K block and the
     // commits.  Descriptors differ only in the 14-bit start-address field.
-    constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockRows, kUnitCols);
+    constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockRows * CG, kUnitCols);
     const uint64_t desc_hi = ptx::smem_desc(0, p.lbo, p.sbo);
     const uint32_t q_base = ptx::smem_u32(q_sm) >> 4, st_base = ptx::smem_u32(stage_sm) >> 4;
     Ring st, acc;
@@ -235,6 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           fail(kErrMmaQFull);
           break;
         }
+        if (CG == 2 && !__all_sync(0xffffffffu, ptx::mbar_wait(pqfull_bar, (uint32_t)(seg & 1)))) {
+          fail(kErrMmaPeerQFull);
+          break;
+        }
         ++seg;
       }
       ptx::tc_fence_after();
@@ -245,16 +301,26 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           ok = false;
           break;
         }
+        if (CG == 2 && !__all_sync(0xffffffffu, ptx::mbar_wait(pfull_bar(st.idx), st.phase))) {
+          fail(kErrMmaPeerFull);
+          ok = false;
+          break;
+        }
         ptx::tc_fence_after();
         const uint32_t e_lo = st_base + (uint32_t)(st.idx * (kStageBytes >> 4));
         const uint32_t q_lo = QRES ? q_base + (uint32_t)(kb * (kKBlockBytes >> 4))
-                                   : e_lo + (uint32_t)(kUnitBlocks * (kKBlockBytes >> 4));
+                                   : e_lo + (uint32_t)(kSlabsPerStage * (kKBlockBytes >> 4));
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kKBlockElems / 16; ++k)  // +32 bytes per K step inside the swizzled row
-            ptx::umma_bf16(d_tmem, desc_hi | (uint64_t)((q_lo + 2u * k) & 0x3fffu),
-                           desc_hi | (uint64_t)((e_lo + 2u * k) & 0x3fffu), idesc, (kb | k) != 0 ? 1u : 0u);
-          ptx::umma_commit(empty_bar(st.idx));  // smem stage reusable once these MMAs retire
+          for (int k = 0; k < kKBlockElems / 16; ++k) {  // +32 bytes per K step inside the swizzled row
+            const uint64_t da = desc_hi | (uint64_t)((q_lo + 2u * k) & 0x3fffu);
+            const uint64_t db = desc_hi | (uint64_t)((e_lo + 2u * k) & 0x3fffu);
+            if (CG == 2) ptx::umma_bf16_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else ptx::umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          // smem stage reusable (in both CTAs) once these MMAs retire
+          if (CG == 2) ptx::umma_commit_2cta(empty_bar(st.idx), 3);
+          else ptx::umma_commit(empty_bar(st.idx));
         }
         __syncwarp();
         st.advance(p.n_stages);
@@ -262,8 +328,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       if (!ok) break;
       const bool seg_end = (u + 1 == u1) || (b + 1 == p.nblk);
       if (ptx::elect_one()) {
-        ptx::umma_commit(tfull_bar(acc.idx));              // accumulator complete -> epilogue
-        if (QRES && seg_end) ptx::umma_commit(qempty_bar);  // query tile no longer read
+        if (CG == 2) {
+          ptx::umma_commit_2cta(tfull_bar(acc.idx), 3);              // accumulators complete -> both epilogues
+          if (QRES && seg_end) ptx::umma_commit_2cta(qempty_bar, 3);  // query tiles no longer read
+        } else {
+          ptx::umma_commit(tfull_bar(acc.idx));
+          if (QRES && seg_end) ptx::umma_commit(qempty_bar);
+        }
       }
       __syncwarp();
       acc.advance(kAccStages);
@@ -278,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     float* my_side = side_ring + ew * (2 * kColsPerWarp);
     Ring acc;
     int slot = 0;
-    int qt = (int)(u0 / p.nblk), b = (int)(u0 % p.nblk);
+    int qt = (int)(u0 / p.nblk) * CG + rank, b = (int)(u0 % p.nblk);
     typename SelectorFor<KSEL>::type top;
     const uint64_t keep_policy = ptx::policy_evict_last();
     float thr = INFINITY;
@@ -296,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         const int64_t q = (int64_t)qt * kBlockRows + lane_q;
         const bool q_ok = q < p.n_queries;
         q_sd = q_ok ? p.q_side[q] : 0.f;
-        const int64_t c_first = cta_of_unit((int64_t)qt * p.nblk, p.total_units, G);
+        const int64_t c_first = cta_of_unit((int64_t)(qt / CG) * p.nblk, p.total_units, G);
         const int list = (int)(c - c_first) * kColSplit + ch;
         const int64_t o = q_ok ? (q * p.n_lists + list) * p.ksel : 0;
         // seeded threshold: the k-th best score over a sample of the corpus (found by an earlier
@@ -320,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       int nb = b + 1, nqt = qt;
       if (nb == p.nblk) {
         nb = 0;
-        ++nqt;
+        nqt += CG;
       }
       float ns[kColsPerWarp / 32];
 #pragma unroll
@@ -406,7 +477,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc.idx));
+      if (lane == 0) {  // the accumulator stage goes back to the (leader's) MMA warp
+        if (CG == 2 && rank != 0) ptx::mbar_arrive_remote(tempty_bar(acc.idx), 0);
+        else ptx::mbar_arrive(tempty_bar(acc.idx));
+      }
       acc.advance(kAccStages);
       if constexpr (SelectorFor<KSEL>::type::kAppend) {
         // routine compactions run here, after the accumulator went back to the MMA warp, a few
@@ -433,37 +507,68 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 
   // ===================== teardown =====================
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();  // nobody touches the peer's barriers or TMEM any more
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) ptx::tmem_dealloc2(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 inline int n_kblocks(const TileGeom& g) { return g.kblocks; }
 inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
-inline int n_stages_for(const TileGeom& g) {
-  const int stage = (q_resident(g) ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
+inline int stage_bytes_for(const TileGeom& g, int cg) {
+  return (kUnitBlocks / cg + (q_resident(g) ? 0 : 1)) * kKBlockBytes;
+}
+inline int n_stages_for(const TileGeom& g, int cg) {
   const int q_bytes = q_resident(g) ? n_kblocks(g) * kKBlockBytes : 0;
-  int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage;
+  int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage_bytes_for(g, cg);
   return s > kMaxStages ? kMaxStages : s;
 }
 inline int ksel_for(int k) { return k <= 10 ? 10 : kBufCap; }  // sorted register list / append buffer
 
+// CTA pairs (cta_group::2) once there are at least two query tiles to pair up; single CTAs for
+// the bandwidth-bound case of one query tile.
+inline int cta_group_for(int64_t n_queries, int sm_count) {
+  if (const char* e = getenv("LK_CG")) {  // bring-up override
+    const int v = atoi(e);
+    if (v == 1 || (v == 2 && sm_count % 2 == 0)) return v;
+  }
+  return n_queries > kBlockRows && sm_count % 2 == 0 ? 2 : 1;
+}
+
+struct Schedule {
+  int cg;            // CTAs per scheduling group
+  int64_t nblk;      // units (256 corpus rows) per query-tile group
+  int64_t nqg;       // query-tile groups (cg tiles each)
+  int64_t total;     // units over all groups
+  int64_t groups;    // scheduling groups launched
+};
+inline Schedule schedule_for(int64_t n_rows, int64_t n_queries, int sm_count) {
+  Schedule s;
+  s.cg = cta_group_for(n_queries, sm_count);
+  s.nblk = (n_rows + kUnitCols - 1) / kUnitCols;
+  const int64_t nqt = (n_queries + kBlockRows - 1) / kBlockRows;
+  s.nqg = (nqt + s.cg - 1) / s.cg;
+  s.total = s.nblk * s.nqg;
+  const int64_t avail = sm_count / s.cg;
+  s.groups = s.total < avail ? s.total : avail;
+  return s;
+}
+
 }  // namespace
 
 int umma_supported(const TileGeom& g, int k) {
-  return g.elem_bytes == 2 && g.kblocks >= 1 && k >= 1 && k <= kMaxK && n_stages_for(g) >= 2;
+  return g.elem_bytes == 2 && g.kblocks >= 1 && k >= 1 && k <= kMaxK && n_stages_for(g, 1) >= 2;
 }
 
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
-  const int64_t nblk = (a.n_rows + kUnitCols - 1) / kUnitCols;  // units (row-block pairs) per query tile
-  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
-  const int64_t total = nblk * nqt;
-  const int64_t grid = total < sm_count ? total : sm_count;
+  const Schedule sc = schedule_for(a.n_rows, a.n_queries, sm_count);
   int64_t maxc = 1;
-  for (int64_t qt = 0; qt < nqt; ++qt) {
-    const int64_t cf = cta_of_unit(qt * nblk, total, grid), cl = cta_of_unit((qt + 1) * nblk - 1, total, grid);
+  for (int64_t qg = 0; qg < sc.nqg; ++qg) {
+    const int64_t cf = cta_of_unit(qg * sc.nblk, sc.total, sc.groups),
+                  cl = cta_of_unit((qg + 1) * sc.nblk - 1, sc.total, sc.groups);
     if (cl - cf + 1 > maxc) maxc = cl - cf + 1;
   }
   *n_lists = (int)maxc * kColSplit;
@@ -471,19 +576,18 @@ int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
   return LK_OK;
 }
 
-// Threshold seeding (k > 32, up to 1024 queries): every (CTA, column half) list starts cold, and
-// with few query tiles each list sees only 1/(2 x CTAs) of the rows, so most of what it
+// Threshold seeding (k > 10, 8..1024 queries): every (group, column half) list starts cold, and
+// with few query tiles each list sees only a small share of the rows, so most of what it
 // appends is far from the global top-k.  Searching a short prefix of the corpus first (one unit
-// = 256 rows per CTA: every list takes at most 128 entries and never compacts) gives every list
-// a threshold that only k * rows / prefix_rows rows of the whole corpus beat.
+// = 256 rows per group: every list takes at most 128 entries and never compacts) gives every
+// list a threshold that only k * rows / prefix_rows rows of the whole corpus beat.
 int64_t umma_seed_rows(const SearchArgs& a, int sm_count) {
   if (ksel_for(a.k) != kBufCap || a.n_queries < 8 || a.n_queries > 1024) return 0;
   if (const char* e = getenv("LK_SEED"))  // bring-up override
     if (!atoi(e)) return 0;
-  const int64_t units = (a.n_rows + kUnitCols - 1) / kUnitCols;
-  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
-  const int64_t s_units = (sm_count + nqt - 1) / nqt;  // one unit per CTA: no list can fill up
-  if (units < 16 * s_units) return 0;
+  const Schedule sc = schedule_for(a.n_rows, a.n_queries, sm_count);
+  const int64_t s_units = (sm_count / sc.cg + sc.nqg - 1) / sc.nqg;  // one unit per group
+  if (sc.nblk < 16 * s_units) return 0;
   return s_units * kUnitCols;
 }
 
@@ -493,18 +597,17 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     set_error("tcgen05 search: unsupported shape (dim_pad=%d, k=%d)", a.g.dim_pad, a.k);
     return LK_ERR_UNSUPPORTED;
   }
-  const int64_t nblk = (a.n_rows + kUnitCols - 1) / kUnitCols;  // units (row-block pairs) per query tile
-  const int64_t nqt = (a.n_queries + kBlockRows - 1) / kBlockRows;
+  const Schedule sc = schedule_for(a.n_rows, a.n_queries, sm_count);
   UmmaParams p;
   p.tiles = static_cast<const unsigned char*>(a.tiles);
   p.side = a.side;
   p.q_tiles = static_cast<const unsigned char*>(a.q_tiles);
   p.q_side = a.q_side;
   p.n_queries = a.n_queries;
-  p.total_units = nblk * nqt;
-  p.nblk = (int)nblk;
+  p.total_units = sc.total;
+  p.nblk = (int)sc.nblk;
   p.nkb = n_kblocks(a.g);
-  p.n_stages = n_stages_for(a.g);
+  p.n_stages = n_stages_for(a.g, sc.cg);
   p.n_lists = a.n_lists;
   p.ksel = a.ksel;
   p.k = a.k;
@@ -520,26 +623,45 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.sbo = kSbo;
   if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
   if (const char* e = getenv("LK_UMMA_SBO")) p.sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("LK_UMMA_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= p.n_stages) p.n_stages = v;
+  }
   const bool qres = q_resident(a.g);
-  const int stage = (qres ? kUnitBlocks : kUnitBlocks + 1) * kKBlockBytes;
   const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
-                      (size_t)p.n_stages * stage;
-  const int64_t grid = p.total_units < sm_count ? p.total_units : sm_count;
+                      (size_t)p.n_stages * stage_bytes_for(a.g, sc.cg);
   const int ksel = ksel_for(a.k);
   if (ksel != a.ksel) {
     set_error("tcgen05 search: plan mismatch (ksel %d vs %d)", a.ksel, ksel);
     return LK_ERR_INVALID;
   }
-#define LK_UMMA(KS, MET, QR)                                                                         \
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(sc.groups * sc.cg));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)sc.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define LK_UMMA(KS, MET, QR, CGV)                                                                    \
   do {                                                                                               \
-    LK_CUDA(cudaFuncSetAttribute(umma_search_kernel<KS, MET, QR>,                                    \
+    LK_CUDA(cudaFuncSetAttribute(umma_search_kernel<KS, MET, QR, CGV>,                               \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    umma_search_kernel<KS, MET, QR><<<(unsigned)grid, kThreads, smem, st>>>(p);                      \
+    LK_CUDA(cudaLaunchKernelEx(&cfg, umma_search_kernel<KS, MET, QR, CGV>, p));                      \
+  } while (0)
+#define LK_UMMA_C(KS, MET, QR)                                             \
+  do {                                                                     \
+    if (sc.cg == 2) LK_UMMA(KS, MET, QR, 2);                               \
+    else LK_UMMA(KS, MET, QR, 1);                                          \
   } while (0)
 #define LK_UMMA_M(KS, QR)                                                  \
   do {                                                                     \
-    if (a.metric == LK_COSINE) LK_UMMA(KS, LK_COSINE, QR);                 \
-    else LK_UMMA(KS, LK_EUCLIDEAN, QR);                                    \
+    if (a.metric == LK_COSINE) LK_UMMA_C(KS, LK_COSINE, QR);               \
+    else LK_UMMA_C(KS, LK_EUCLIDEAN, QR);                                  \
   } while (0)
   if (ksel == 10) {
     if (qres) LK_UMMA_M(10, true); else LK_UMMA_M(10, false);
@@ -547,6 +669,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);  // KSEL 0 = BufSelector
   }
 #undef LK_UMMA_M
+#undef LK_UMMA_C
 #undef LK_UMMA
   LK_CHECK_LAUNCH("umma_search_kernel");
   return LK_OK;

@@ -1,10 +1,10 @@
 #!/bin/bash
 set -u
-for B in 64 4096; do
-echo "== k10 B=$B"; python tools/prof_case.py --rows 10000000 --dim 384 --batch $B --k 10 --iters 3 2>&1 | tail -1
-echo "== k32 B=$B"; python tools/prof_case.py --rows 10000000 --dim 384 --batch $B --k 32 --iters 3 2>&1 | tail -1
-echo "== k100 B=$B"; python tools/prof_case.py --rows 10000000 --dim 384 --batch $B --k 100 --iters 3 2>&1 | tail -1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "umma_kernel or large or sharding" 2>&1 | tail -3
+for D in 384 768; do
+for B in 256 4096; do
+C="python tools/prof_case.py --rows 10000000 --dim $D --batch $B --k 10 --iters 4"
+echo "== D=$D B=$B cg=2"; $C 2>&1 | tail -1
+echo "== D=$D B=$B cg=1"; LK_CG=1 $C 2>&1 | tail -1
 done
-echo "== k100 B=64 noseed"; LK_SEED=0 python tools/prof_case.py --rows 10000000 --dim 384 --batch 64 --k 100 --iters 3 2>&1 | tail -1
-echo "== k100 B=1024"; python tools/prof_case.py --rows 10000000 --dim 384 --batch 1024 --k 100 --iters 3 2>&1 | tail -1
-echo "== k10 B=1024"; python tools/prof_case.py --rows 10000000 --dim 384 --batch 1024 --k 10 --iters 3 2>&1 | tail -1
+done
