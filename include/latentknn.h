@@ -48,6 +48,10 @@ typedef enum lk_ae_kind { LK_AE_DAE = 0, LK_AE_CAE = 1, LK_AE_VAE_MU = 2 } lk_ae
 
 typedef struct lk_index lk_index;
 typedef struct lk_ae lk_ae;
+typedef struct lk_comm lk_comm;
+
+#define LK_MAX_WORLD 16         /* ranks of one candidate exchange (one NVLink domain) */
+#define LK_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 
 /* ---- library ----------------------------------------------------------------------- */
 int lk_abi_version(void);
@@ -113,6 +117,33 @@ int lk_index_set_timing(lk_index* ix, int enabled);
 int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b,
                   int n_lists, int list_len, int k, float* out_scores, int64_t* out_idx,
                   int mem, void* stream);
+
+/* ---- candidate exchange between the GPUs of a row-sharded index, fused with that merge
+ *      (net-new).  One process per GPU.  Every rank owns a symmetric
+ *      buffer; the peers' buffers are mapped through CUDA IPC (the handles travel over the
+ *      host-side process group).  lk_comm_exchange_merge is ONE kernel per rank and call:
+ *      it stores this rank's b x k candidates (global ids) straight into every peer's buffer
+ *      over NVLink, releases per-query flags, waits for the peers' flags and merges the
+ *      world x k candidates of each query.  All ranks must call it in the same order.
+ *
+ *      lk_comm_attach_local / lk_comm_begin / lk_comm_publish / lk_comm_collect split the
+ *      same protocol into steps so that several ranks can be driven from ONE process (tests
+ *      on a single GPU: begin + publish on every rank first, then collect on every rank). */
+int lk_comm_create(lk_comm** out, int device, int rank, int world, int64_t max_b, int max_k);
+/* out_handle: LK_IPC_HANDLE_BYTES bytes identifying this rank's buffer to other processes */
+int lk_comm_ipc_handle(lk_comm* c, void* out_handle);
+/* handles: world x LK_IPC_HANDLE_BYTES bytes, rank-major (the own entry is ignored) */
+int lk_comm_open_peers(lk_comm* c, const void* handles);
+int lk_comm_attach_local(lk_comm* c, int peer_rank, lk_comm* peer);
+int lk_comm_exchange_merge(lk_comm* c, const float* local_scores, const int64_t* local_idx, int64_t b, int k,
+                           float* out_scores, int64_t* out_idx, void* stream);
+int lk_comm_begin(lk_comm* c);
+int lk_comm_publish(lk_comm* c, const float* local_scores, const int64_t* local_idx, int64_t b, int k,
+                    void* stream);
+int lk_comm_collect(lk_comm* c, int64_t b, int k, float* out_scores, int64_t* out_idx, void* stream);
+/* synchronises with the device: LK_ERR_CUDA if a wait for a peer timed out since the last check */
+int lk_comm_check(lk_comm* c);
+int lk_comm_destroy(lk_comm* c);
 
 /* ---- autoencoder encoder forward: replaces DenoisingAutoencoder.encode
  *      (models/denoising_autoencoder.py:33-34), ContrastiveAutoencoder.encode

@@ -9,9 +9,10 @@ from .retrieval import BruteForceRetriever, FAISSEmbeddingRetriever, StatsTracke
 from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, VariationalAutoencoder,
                            load_autoencoder)
 from .sharded import ShardedRetriever, shard_bounds
+from .exchange import PeerExchange
 
 __all__ = [
     "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
-    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange",
 ]

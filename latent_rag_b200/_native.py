@@ -18,6 +18,8 @@ LK_COSINE, LK_EUCLIDEAN, LK_MAHALANOBIS = 0, 1, 2
 LK_KERNEL_AUTO, LK_KERNEL_SIMT, LK_KERNEL_UMMA = 0, 1, 2
 LK_AE_DAE, LK_AE_CAE, LK_AE_VAE_MU = 0, 1, 2
 LK_MAX_K = 128
+LK_MAX_WORLD = 16
+LK_IPC_HANDLE_BYTES = 64
 
 METRICS = {"cosine": LK_COSINE, "euclidean": LK_EUCLIDEAN, "mahalanobis": LK_MAHALANOBIS}
 KERNELS = {"auto": LK_KERNEL_AUTO, "simt": LK_KERNEL_SIMT, "umma": LK_KERNEL_UMMA}
@@ -48,6 +50,16 @@ SYMBOLS = [
     ("lk_ae_set_kernel", c_int, [c_void_p, c_int]),
     ("lk_ae_encode", c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     ("lk_ae_destroy", c_int, [c_void_p]),
+    ("lk_comm_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int]),
+    ("lk_comm_ipc_handle", c_int, [c_void_p, c_void_p]),
+    ("lk_comm_open_peers", c_int, [c_void_p, c_void_p]),
+    ("lk_comm_attach_local", c_int, [c_void_p, c_int, c_void_p]),
+    ("lk_comm_exchange_merge", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("lk_comm_begin", c_int, [c_void_p]),
+    ("lk_comm_publish", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    ("lk_comm_collect", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    ("lk_comm_check", c_int, [c_void_p]),
+    ("lk_comm_destroy", c_int, [c_void_p]),
 ]
 
 

@@ -4,8 +4,12 @@ Net-new relative to the reference, which is single-process (SURVEY.md section 8e
 owns a contiguous block of corpus rows, runs the fused search on its shard and returns
 GLOBAL row ids (local id + row offset, added in the merge kernel); one all-gather of the
 [B, k] candidates (NCCL over NVLink) and the k-way merge kernel give every rank the global
-top-k.  Queries are replicated.  The only exchange is that all-gather: B * k * 12 bytes per
-rank.
+top-k.  Queries are replicated.  The only exchange is B * k * 12 bytes per rank.
+
+Two exchange paths: "p2p" (default on the native path) -- latent_rag_b200.exchange.PeerExchange,
+one kernel per rank that stores the candidates into every peer's buffer over NVLink, waits for
+the peers' flags and merges; "nccl" -- all_gather_into_tensor + the merge kernel (also the path
+of the CPU tests, over gloo).
 """
 from __future__ import annotations
 
@@ -70,6 +74,8 @@ class ShardedRetriever:
         precision_matrix: Optional[np.ndarray] = None,
         local_search: Optional[Callable] = None,
         merge: Optional[Callable] = None,
+        exchange: str = "auto",
+        max_batch: int = 4096,
     ):
         if metric not in ("cosine", "euclidean", "mahalanobis"):
             raise ValueError(f"Unsupported metric: {metric}")
@@ -105,6 +111,13 @@ class ShardedRetriever:
             torch.cuda.synchronize(device)
             self.comm_device = torch.device(f"cuda:{device}")
             self._local_search = self._native_local_search
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"Unknown exchange: {exchange}")
+        self._xchg = None
+        if self.index is not None and self.world > 1 and exchange in ("auto", "p2p"):
+            from .exchange import PeerExchange
+
+            self._xchg = PeerExchange(self.comm_device.index, self.rank, self.world, max_b=max_batch).connect(group)
         n_total = torch.tensor([self.n_local], dtype=torch.int64, device=self.comm_device)
         if self.world > 1:
             dist.all_reduce(n_total, group=group)
@@ -120,6 +133,8 @@ class ShardedRetriever:
         out_d, out_i = self.search_tensors(queries, k)
         if torch.is_tensor(out_d):
             out_d, out_i = out_d.cpu().numpy(), out_i.cpu().numpy()
+        if self._xchg is not None:
+            self._xchg.check()  # a peer that never published shows up here, not as a hang
         b = 1 if queries.dim() == 1 else queries.size(0)
         self._stats.add_search_batch(batch_size=b, seconds=time.perf_counter() - t0)
         return np.asarray(out_d, dtype=np.float32), np.asarray(out_i, dtype=np.int64)
@@ -132,13 +147,19 @@ class ShardedRetriever:
         b = queries.size(0)
         k = min(int(k), self.n_total)
         # 1. local top-k with global ids, padded to k when the shard is smaller than k
-        d = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.comm_device)
-        i = torch.full((b, k), -1, dtype=torch.int64, device=self.comm_device)
         kl = min(k, self.n_local)
-        if kl > 0 and b > 0:
-            dl, il = self._local_search(queries, kl)
-            d[:, :kl] = torch.as_tensor(dl, device=self.comm_device)
-            i[:, :kl] = torch.as_tensor(il, device=self.comm_device)
+        if kl == k and b > 0 and self._xchg is not None:
+            d, i = self._local_search(queries, k)
+        else:
+            d = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.comm_device)
+            i = torch.full((b, k), -1, dtype=torch.int64, device=self.comm_device)
+            if kl > 0 and b > 0:
+                dl, il = self._local_search(queries, kl)
+                d[:, :kl] = torch.as_tensor(dl, device=self.comm_device)
+                i[:, :kl] = torch.as_tensor(il, device=self.comm_device)
+        # 2+3 fused: candidates go straight into every peer's buffer, flags, wait, merge
+        if self._xchg is not None:
+            return self._xchg.exchange_merge(d, i, k)
         # 2. the one exchange step: all-gather of the candidates
         if self.world > 1:
             gd = torch.empty((self.world * b, k), dtype=torch.float32, device=self.comm_device)

@@ -1,5 +1,6 @@
-"""Row-sharded search over 2 GPUs through NCCL (skipped on a one-GPU box): every rank must
-return the global top-k of the oracle."""
+"""Row-sharded search over 2 GPUs (skipped on a one-GPU box), candidates exchanged either by the
+fused peer-to-peer kernel over NVLink or by an NCCL all-gather: every rank must return the
+global top-k of the oracle, repeatedly (the exchange buffers alternate between calls)."""
 import os
 import socket
 import sys
@@ -27,7 +28,7 @@ def _data(metric):
     return emb, q
 
 
-def _worker(rank, world, port, metric, k, out_dir):
+def _worker(rank, world, port, metric, k, exchange, out_dir):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -38,21 +39,26 @@ def _worker(rank, world, port, metric, k, out_dir):
 
         emb, q = _data(metric)
         lo, hi = lrb.shard_bounds(len(emb), world)[rank]
-        r = lrb.ShardedRetriever(emb[lo:hi].cuda(), lo, metric, device=rank)
+        r = lrb.ShardedRetriever(emb[lo:hi].cuda(), lo, metric, device=rank, exchange=exchange, max_batch=64)
         assert r.n_total == len(emb)
-        d, i = r.search(q.cuda(), k)
+        assert (r._xchg is not None) == (exchange == "p2p")
+        d, i = r.search(q.cuda(), k)  # 130 queries: three exchange rounds of at most 64
+        for rep in range(3):          # the two buffer slots get reused
+            d1, i1 = r.search(q[:5 + rep].cuda(), k)
+            np.testing.assert_array_equal(i1, i[:5 + rep])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), d=d, i=i)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("metric,k", [("cosine", 10), ("euclidean", 32), ("mahalanobis", 10)])
-def test_nccl_sharded_search(tmp_path, metric, k):
+def test_sharded_search_two_gpus(tmp_path, metric, k, exchange):
     import oracle
 
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, metric, k, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, metric, k, exchange, str(tmp_path)), nprocs=2, join=True)
     emb, q = _data(metric)
     if metric == "mahalanobis":
         p = oracle.mahalanobis_precision(emb)

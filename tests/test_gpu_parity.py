@@ -426,6 +426,36 @@ def test_merge_selection_with_massive_ties(lrb):
     np.testing.assert_array_equal(d, d_ref)
 
 
+@pytest.mark.parametrize("world,b,k", [(2, 1, 10), (8, 70, 10), (3, 300, 100), (16, 5, 128)])
+def test_peer_exchange_protocol_on_one_gpu(lrb, world, b, k):
+    """The peer-to-peer candidate exchange with every rank driven from this process on one GPU:
+    all ranks publish, then all ranks collect (the fused kernel does both in one launch per rank
+    and needs one GPU per rank: tests/test_gpu_multi.py).  Repeated so that both buffer slots
+    and growing epochs are used."""
+    rng = np.random.default_rng(world * 100 + b)
+    comms = [lrb.PeerExchange(0, r, world, max_b=512, max_k=128) for r in range(world)]
+    for c in comms:
+        c.attach_local(comms)
+    for rep in range(3):
+        cd = rng.standard_normal((b, world, k)).astype(np.float32)
+        cd = -np.sort(-cd, axis=2)
+        ci = rng.permutation(b * world * k).reshape(b, world, k).astype(np.int64)
+        ci[:, -1, -3:] = -1  # a short shard pads with -1 / -inf
+        cd[:, -1, -3:] = -np.inf
+        cd[0, 0, 0] = cd[0, 1 % world, 0]  # a tie across ranks
+        for r, c in enumerate(comms):
+            c.begin()
+            c.publish(torch.from_numpy(cd[:, r]).cuda(), torch.from_numpy(ci[:, r]).cuda())
+        d_ref, i_ref = oracle.merge_topk(cd, ci, k)
+        for c in comms:
+            d, i = c.collect(b, k)
+            c.check()
+            np.testing.assert_array_equal(i.cpu().numpy(), i_ref)
+            np.testing.assert_array_equal(d.cpu().numpy(), d_ref)
+    for c in comms:
+        c.close()
+
+
 @pytest.mark.parametrize("world", [1, 2, 8])
 def test_row_sharding_is_invisible(lrb, world):
     """Searching `world` row shards (global ids via idx_base) and merging equals the unsharded
