@@ -85,6 +85,7 @@ struct UmmaParams {
   float* debug_tile;     // [128 queries][128 rows] raw dot products of unit 0, or null
   uint32_t lbo, sbo;
   int dbg;
+  int rotate;            // corpus rotation per query-tile group (rot_cut)
 };
 
 __host__ __device__ inline int64_t unit_begin(int64_t c, int64_t total, int64_t grid) {
@@ -93,6 +94,25 @@ __host__ __device__ inline int64_t unit_begin(int64_t c, int64_t total, int64_t 
 // the CTA whose range contains unit u
 __host__ __device__ inline int64_t cta_of_unit(int64_t u, int64_t total, int64_t grid) {
   return ((u + 1) * grid - 1) / total;
+}
+
+// Corpus rotation.  Unit b of query-tile group qg works on corpus row-block pair
+// (b - cut(qg)) mod nblk, where cut(qg) is the offset of the first scheduling-group boundary
+// inside qg's unit range.  Every scheduling group that lies wholly inside one query-tile group
+// then STARTS at a multiple of the per-group share of the corpus, so groups working for
+// different query tiles stream the same row blocks at the same time and HBM sees the corpus
+// about (1 + leftovers) times per batch instead of once per query-tile group and L2 sharing
+// set.  A group boundary sits exactly at the wrap point, so the rows of every (group, query
+// tile) segment are still visited in ascending order (the tie rule relies on it).
+__host__ __device__ inline int64_t rot_cut(int64_t qg, int64_t nblk, int64_t total, int64_t grid) {
+  const int64_t x = qg * nblk;
+  const int64_t c = (x * grid + total - 1) / total;  // first group starting at or after x
+  return c * total / grid - x;
+}
+__host__ __device__ inline int rot_block(int64_t qg, int b, int64_t nblk, int64_t total, int64_t grid, int rotate) {
+  if (!rotate) return b;
+  int cb = b - (int)rot_cut(qg, nblk, total, grid);
+  return cb < 0 ? cb + (int)nblk : cb;
 }
 
 struct Ring {
@@ -186,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     Ring st;
     int seg = 0;
     int qt = (int)(u0 / p.nblk) * CG + rank, b = (int)(u0 % p.nblk);
+    int cb = rot_block(u0 / p.nblk, b, p.nblk, p.total_units, G, p.rotate);  // corpus row-block pair of unit b
     bool ok = true;
     // one query tile = every row block is read exactly once: stream it evict-first so that the
     // query tile and the partial lists stay in L2; with several query tiles the row blocks are
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         __syncwarp();
         ++seg;
       }
-      const unsigned char* e_src = p.tiles + (int64_t)b * kUnitBlocks * p.block_bytes;
+      const unsigned char* e_src = p.tiles + (int64_t)cb * kUnitBlocks * p.block_bytes;
       for (int kb = 0; kb < p.nkb; ++kb) {
         if (!__all_sync(0xffffffffu, ptx::mbar_wait(empty_bar(st.idx), st.phase ^ 1u))) {
           fail(kErrProdEmpty);
@@ -231,9 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         __syncwarp();
         st.advance(p.n_stages);
       }
+      if (++cb == p.nblk) cb = 0;
       if (++b == p.nblk) {
         b = 0;
         qt += CG;
+        cb = rot_block(qt / CG, 0, p.nblk, p.total_units, G, p.rotate);
       }
     }
   } else if (warp == 1 && CG == 2 && rank != 0) {
@@ -350,6 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     Ring acc;
     int slot = 0;
     int qt = (int)(u0 / p.nblk) * CG + rank, b = (int)(u0 % p.nblk);
+    int cb = rot_block(u0 / p.nblk, b, p.nblk, p.total_units, G, p.rotate);  // corpus row-block pair of unit b
     typename SelectorFor<KSEL>::type top;
     const uint64_t keep_policy = ptx::policy_evict_last();
     float thr = INFINITY;
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     int* cnt_out = nullptr;
     bool seg_start = true;
     if (u0 < u1) {
-      const float* sp = p.side + (int64_t)b * kUnitCols + ch * kColsPerWarp;
+      const float* sp = p.side + (int64_t)cb * kUnitCols + ch * kColsPerWarp;
 #pragma unroll
       for (int j = 0; j < kColsPerWarp / 32; ++j) my_side[lane + 32 * j] = sp[lane + 32 * j];
       __syncwarp();
@@ -388,16 +412,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         seg_start = false;
       }
       // prefetch the next unit's side values while this unit's MMAs finish
-      int nb = b + 1, nqt = qt;
+      int nb = b + 1, nqt = qt, ncb = cb + 1 == p.nblk ? 0 : cb + 1;
       if (nb == p.nblk) {
         nb = 0;
         nqt += CG;
+        ncb = rot_block(nqt / CG, 0, p.nblk, p.total_units, G, p.rotate);
       }
       float ns[kColsPerWarp / 32];
 #pragma unroll
       for (int j = 0; j < kColsPerWarp / 32; ++j) ns[j] = 0.f;
       if (u + 1 < u1) {
-        const float* sp = p.side + (int64_t)nb * kUnitCols + ch * kColsPerWarp;
+        const float* sp = p.side + (int64_t)ncb * kUnitCols + ch * kColsPerWarp;
 #pragma unroll
         for (int j = 0; j < kColsPerWarp / 32; ++j) ns[j] = sp[lane + 32 * j];
       }
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       }
       ptx::tc_fence_after();
       const float* sd = my_side + slot * kColsPerWarp;
-      const int32_t row0 = b * kUnitCols + ch * kColsPerWarp;
+      const int32_t row0 = cb * kUnitCols + ch * kColsPerWarp;
       // Fast path (branch-free, a few hundred instructions in total so it stays in the
       // instruction cache): score every column and keep the running max.  Only when some
       // lane's max beats its k-th best does the warp take the slow path, which holds the
@@ -502,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       }
       b = nb;
       qt = nqt;
+      cb = ncb;
     }
   }
 
@@ -619,6 +645,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.seed = a.seed;
   p.debug_tile = a.debug_tile;
   p.dbg = getenv("LK_DBG") ? atoi(getenv("LK_DBG")) : 0;
+  p.rotate = (p.dbg & 4) ? 0 : 1;
   p.lbo = kLbo;
   p.sbo = kSbo;
   if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
