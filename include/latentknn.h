@@ -118,6 +118,15 @@ int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx,
                   int n_lists, int list_len, int k, float* out_scores, int64_t* out_idx,
                   int mem, void* stream);
 
+/* ---- document-level MaxSim aggregation: replaces the per-query Python loop of the
+ *      reference's caller (main.py:270-282).  cand_* are b x cand_k search results (best
+ *      first, row ids; < 0 = padding), row_doc_ids maps a corpus row (chunk) to its document;
+ *      out_* are b x top_k: the documents ranked by their best chunk, ties in first-seen
+ *      order, padded with doc id -1 / score -inf.  All pointers are device memory. */
+int lk_maxsim_rerank(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b, int cand_k,
+                     const int64_t* row_doc_ids, int64_t n_rows, int top_k, float* out_scores,
+                     int64_t* out_doc_ids, void* stream);
+
 /* ---- candidate exchange between the GPUs of a row-sharded index, fused with that merge
  *      (net-new).  One process per GPU.  Every rank owns a symmetric
  *      buffer; the peers' buffers are mapped through CUDA IPC (the handles travel over the

@@ -50,6 +50,8 @@ SYMBOLS = [
     ("lk_ae_set_kernel", c_int, [c_void_p, c_int]),
     ("lk_ae_encode", c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     ("lk_ae_destroy", c_int, [c_void_p]),
+    ("lk_maxsim_rerank", c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,
+                                 c_void_p, c_void_p]),
     ("lk_comm_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int]),
     ("lk_comm_ipc_handle", c_int, [c_void_p, c_void_p]),
     ("lk_comm_open_peers", c_int, [c_void_p, c_void_p]),

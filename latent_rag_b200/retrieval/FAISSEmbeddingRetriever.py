@@ -19,13 +19,13 @@ import numpy as np
 import torch
 
 from ..engine import ExactIndex
-from .common import StatsTracker
+from .common import BatchedRetrieveMixin, StatsTracker
 
 _INDEX_TYPES = ("flatip", "hnsw", "ivfpq")
 _MAGIC = b"LKNNIDX1"
 
 
-class FAISSEmbeddingRetriever:
+class FAISSEmbeddingRetriever(BatchedRetrieveMixin):
     def __init__(
         self,
         embedding_dim: int,
@@ -229,6 +229,25 @@ class FAISSEmbeddingRetriever:
         dd, ii = self.index.search(queries, kk)
         self._stats.add_search_batch(batch_size=b, seconds=time.perf_counter() - t0)
         d[:, :kk], i[:, :kk] = dd, ii
+        return d, i
+
+    def _search_device(self, queries: torch.Tensor, k: int):
+        """`search` that leaves (scores, row ids) on the device, clamped to the rows present: for
+        retrieve_batch."""
+        if isinstance(queries, np.ndarray):
+            queries = torch.from_numpy(queries)
+        if queries.dim() == 1:
+            queries = queries.unsqueeze(0)
+        if not self._doc_ids:
+            self._load_metadata()
+        kk = min(int(k), self.index.size)
+        dev = torch.device(f"cuda:{self.index.device}")
+        if queries.size(0) == 0 or kk < 1:
+            return (torch.empty((queries.size(0), max(kk, 0)), dtype=torch.float32, device=dev),
+                    torch.empty((queries.size(0), max(kk, 0)), dtype=torch.int64, device=dev))
+        t0 = time.perf_counter()
+        d, i = self.index.search(queries, kk, device_out=True)
+        self._stats.add_search_batch(batch_size=queries.size(0), seconds=time.perf_counter() - t0)
         return d, i
 
     def retrieve(self, query_emb: torch.Tensor, top_k: int = 10) -> Tuple[List[str], List[float], List[int]]:

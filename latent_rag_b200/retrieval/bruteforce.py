@@ -12,12 +12,12 @@ import torch
 import torch.nn.functional as F
 
 from ..engine import ExactIndex
-from .common import StatsTracker, empirical_precision, whitener_from_precision
+from .common import BatchedRetrieveMixin, StatsTracker, empirical_precision, whitener_from_precision
 
 Similarity = Literal["cosine", "euclidean", "mahalanobis"]
 
 
-class BruteForceRetriever:
+class BruteForceRetriever(BatchedRetrieveMixin):
     """Exact retriever with performance metrics (reference: retrieval/bruteforce.py:17-24).
 
     Positional arguments are the reference's: `embeddings [N, D]`, `texts`, `doc_ids`,
@@ -98,6 +98,22 @@ class BruteForceRetriever:
                     np.empty((queries.size(0), max(k, 0)), dtype=np.int64))
         t0 = time.perf_counter()
         d, i = self.index.search(queries, k)
+        self._stats.add_search_batch(batch_size=len(queries), seconds=time.perf_counter() - t0)
+        return d, i
+
+    def _search_device(self, queries: torch.Tensor, k: int):
+        """`search` that leaves (scores, row ids) on the device: for retrieve_batch."""
+        if isinstance(queries, np.ndarray):
+            queries = torch.from_numpy(queries)
+        if queries.dim() == 1:
+            queries = queries.unsqueeze(0)
+        k = min(int(k), self.index.size)
+        dev = torch.device(f"cuda:{self.index.device}")
+        if k < 1 or queries.size(0) == 0:
+            return (torch.empty((queries.size(0), max(k, 0)), dtype=torch.float32, device=dev),
+                    torch.empty((queries.size(0), max(k, 0)), dtype=torch.int64, device=dev))
+        t0 = time.perf_counter()
+        d, i = self.index.search(queries, k, device_out=True)
         self._stats.add_search_batch(batch_size=len(queries), seconds=time.perf_counter() - t0)
         return d, i
 

@@ -3,7 +3,7 @@ reference (retrieval/common.py:37-65) and Mahalanobis statistics.  No search ari
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
@@ -67,3 +67,54 @@ def whitener_from_precision(precision: np.ndarray) -> np.ndarray:
     form (q-e)^T P (q-e) into a squared Euclidean distance."""
     p = np.asarray(precision, dtype=np.float64)
     return np.linalg.cholesky(0.5 * (p + p.T))
+
+
+class BatchedRetrieveMixin:
+    """`retrieve_batch`: the reference caller's hot loop (main.py:264-282) as two device calls --
+    one search at `candidate_k` for the whole query batch and the document-level MaxSim
+    aggregation kernel -- instead of one `retrieve` + dict + sort per query in Python.
+
+    Needs `self.index` (ExactIndex), `self.doc_ids` / `self._doc_ids` (row -> document id) and the
+    class's own query preparation through `_search_device(queries, k)`.
+    """
+
+    _row_doc_dev = None
+    _row_doc_len = -1
+
+    def _row_doc_ids(self):
+        return self.doc_ids if hasattr(self, "doc_ids") else self._doc_ids
+
+    def _row_doc_tensor(self, device):
+        ids = self._row_doc_ids()
+        if self._row_doc_dev is None or self._row_doc_len != len(ids) or self._row_doc_dev.device != device:
+            self._row_doc_dev = torch.as_tensor(np.asarray(ids, dtype=np.int64)).to(device)
+            self._row_doc_len = len(ids)
+        return self._row_doc_dev
+
+    def retrieve_batch(self, query_embeddings, top_k: int = 10, candidate_k: Optional[int] = None):
+        """-> (doc_ids List[List[int]], scores List[List[float]]): per query the `top_k` documents
+        ranked by their best chunk among the `candidate_k` nearest chunks (main.py:264-282:
+        candidate_k defaults to top_k; the reference uses 3 * top_k when chunking)."""
+        from ctypes import c_void_p
+
+        from .. import _native as nat
+
+        candidate_k = int(top_k if candidate_k is None else candidate_k)
+        d, i = self._search_device(query_embeddings, candidate_k)  # CUDA tensors [B, ck]
+        b, ck = d.shape
+        top_k = min(int(top_k), ck)
+        if b == 0 or ck == 0:
+            return [[] for _ in range(b)], [[] for _ in range(b)]
+        dev = d.device
+        row_doc = self._row_doc_tensor(dev)
+        out_s = torch.empty((b, top_k), dtype=torch.float32, device=dev)
+        out_d = torch.empty((b, top_k), dtype=torch.int64, device=dev)
+        lib = nat.load()
+        nat.check(lib.lk_maxsim_rerank(dev.index, c_void_p(d.data_ptr()), c_void_p(i.data_ptr()), b, ck,
+                                       c_void_p(row_doc.data_ptr()), row_doc.numel(), top_k,
+                                       c_void_p(out_s.data_ptr()), c_void_p(out_d.data_ptr()),
+                                       c_void_p(int(torch.cuda.current_stream(dev).cuda_stream))),
+                  "lk_maxsim_rerank")
+        ids, sc = out_d.cpu().numpy(), out_s.cpu().numpy()
+        keep = np.isfinite(sc)  # padding: fewer documents than top_k among the candidates
+        return ([ids[r][keep[r]].tolist() for r in range(b)], [sc[r][keep[r]].tolist() for r in range(b)])

@@ -68,3 +68,17 @@ def evaluate_retrieval(
         std = math.sqrt(sum((v - mean) ** 2 for v in vals) / (q - 1)) if q > 1 else 0.0
         out[m] = {"mean": float(mean), "std": float(std)}
     return out
+
+
+def maxsim_rerank(scores_k, docids_k, top_k: int):
+    """Document-level MaxSim aggregation of one query's candidates, as the reference's caller
+    does it (main.py:273-282): best score per doc id, documents sorted by it (descending,
+    Python's stable sort: ties stay in first-seen order), truncated to top_k.
+    -> (ranked doc ids, their scores)."""
+    agg = {}
+    for did, sc in zip(docids_k, scores_k):
+        prev = agg.get(did)
+        if (prev is None) or (sc > prev):
+            agg[did] = sc
+    ranked = sorted(agg, key=agg.get, reverse=True)[:top_k]
+    return ranked, [agg[d] for d in ranked]

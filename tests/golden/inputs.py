@@ -62,3 +62,15 @@ def metrics_case(q: int = 40, k: int = 10, universe: int = 60) -> Tuple[List[Lis
     retrieved = [rng.permutation(universe)[:k].tolist() for _ in range(q)]
     relevant = [rng.permutation(universe)[: int(rng.integers(1, 4))].tolist() for _ in range(q)]
     return retrieved, relevant
+
+
+def maxsim_case(q: int = 30, ck: int = 30, docs: int = 12, seed: int = 91):
+    """Candidates of `q` queries for the document-level MaxSim aggregation (main.py:264-282):
+    descending scores with some exact ties, chunk -> doc ids with repeats.
+    -> (scores [q, ck] float32, doc ids [q, ck] int64)"""
+    rng = np.random.default_rng(seed)
+    sc = -np.sort(-rng.standard_normal((q, ck)).astype(np.float32), axis=1)
+    sc[::3, 4] = sc[::3, 3]  # equal scores: the stable sort keeps first-seen order
+    did = rng.integers(0, docs, size=(q, ck)).astype(np.int64)
+    did[1] = np.arange(ck) % 3  # only three documents among the candidates: fewer than top_k
+    return sc, did

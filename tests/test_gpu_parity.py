@@ -394,6 +394,58 @@ def test_latent_pipeline_config2_shape(lrb):
 
 
 # ---------------------------------------------------------------------------------------
+# batched retrieve + document-level MaxSim (the reference caller's loop, main.py:264-282)
+# ---------------------------------------------------------------------------------------
+def test_maxsim_kernel_matches_reference_outputs(lrb):
+    """lk_maxsim_rerank on the seeded candidates whose ranked doc ids the reference's own source
+    lines produced (tests/golden/maxsim_golden.json)."""
+    import json
+    from ctypes import c_void_p
+
+    nat = lrb._native
+    with open(os.path.join(os.path.dirname(__file__), "golden", "maxsim_golden.json")) as f:
+        gold = json.load(f)
+    sc, did = inputs.maxsim_case()
+    q, ck = sc.shape
+    # the kernel maps row ids -> doc ids: use one distinct row per candidate
+    rows = torch.arange(q * ck, dtype=torch.int64).view(q, ck).cuda()
+    row_doc = torch.from_numpy(did.reshape(-1)).cuda()
+    for top_k in (10, 5):
+        out_s = torch.empty((q, top_k), dtype=torch.float32, device="cuda")
+        out_d = torch.empty((q, top_k), dtype=torch.int64, device="cuda")
+        nat.check(nat.load().lk_maxsim_rerank(0, c_void_p(torch.from_numpy(sc).cuda().data_ptr()), c_void_p(rows.data_ptr()),
+                                              q, ck, c_void_p(row_doc.data_ptr()), row_doc.numel(), top_k,
+                                              c_void_p(out_s.data_ptr()), c_void_p(out_d.data_ptr()), None), "lk_maxsim_rerank")
+        got = out_d.cpu().numpy()
+        for g in (g for g in gold if g["top_k"] == top_k):
+            want = g["ranked_docids"]
+            assert got[g["row"], : len(want)].tolist() == want
+            assert (got[g["row"], len(want):] == -1).all()
+
+
+@pytest.mark.parametrize("cls", ["brute", "faiss"])
+def test_retrieve_batch_equals_the_per_query_loop(lrb, cls):
+    """retrieve_batch == the reference caller's loop: retrieve(q, candidate_k) per query, MaxSim
+    per doc id, stable sort, truncate (main.py:264-282), chunked corpus (4 chunks per document)."""
+    rng = np.random.default_rng(21)
+    n, dim, b, top_k = 6000, 64, 150, 10
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(emb[rng.integers(0, n, b)] + 0.3 * torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    doc_ids = (rng.permutation(n) // 4).tolist()
+    if cls == "brute":
+        r = lrb.BruteForceRetriever(emb, [""] * n, doc_ids, metric="cosine")
+    else:
+        r = lrb.FAISSEmbeddingRetriever(dim, index_type="flatip")
+        r.build(emb, [""] * n, doc_ids)
+    got_ids, got_sc = r.retrieve_batch(q, top_k=top_k, candidate_k=3 * top_k)
+    for row in range(b):
+        _, scores_k, docids_k = r.retrieve(q[row], top_k=3 * top_k)
+        want, want_sc = oracle.maxsim_rerank(scores_k, docids_k, top_k)
+        assert got_ids[row] == want
+        np.testing.assert_allclose(got_sc[row], want_sc, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------
 # merge kernel + sharding
 # ---------------------------------------------------------------------------------------
 def test_merge_kernel_matches_oracle(lrb):

@@ -141,3 +141,18 @@ def test_merge_topk_equals_global_topk():
         d, i = oracle.merge_topk(np.concatenate(cd, 1), np.concatenate(ci, 1), 10)
         np.testing.assert_array_equal(i, full_i)
         np.testing.assert_allclose(d, full_d, rtol=1e-6)
+
+
+def test_oracle_maxsim_matches_reference_outputs():
+    """oracle.maxsim_rerank against the ranked doc ids produced by the reference's own source
+    lines (main.py:273-282; tests/golden/make_golden.py::maxsim)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "maxsim_golden.json")) as f:
+        gold = json.load(f)
+    sc, did = inputs.maxsim_case()
+    for g in gold:
+        ranked, scores = oracle.maxsim_rerank(sc[g["row"]].tolist(), did[g["row"]].tolist(), g["top_k"])
+        assert ranked == g["ranked_docids"]
+        assert scores == sorted(scores, reverse=True)
