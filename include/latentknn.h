@@ -105,6 +105,10 @@ int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host,
 int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, int64_t b, int k,
                     float* out_scores, int64_t* out_idx, int out_mem, int64_t idx_base,
                     int kernel, void* stream);
+/* With device outputs lk_index_search returns without synchronising; this waits for the device
+ * and reports a search kernel whose bounded pipeline waits timed out since the last check
+ * (LK_ERR_CUDA; with host outputs lk_index_search checks by itself). */
+int lk_index_check(lk_index* ix);
 /* device time (ms, CUDA events on `stream`) of the search kernel proper and of the whole
  * device side (query prep + search + merge) of the last lk_index_search on this handle;
  * used for StatsTracker (retrieval/common.py:37-65) and for bench.py's roofline. */

@@ -38,6 +38,7 @@ SYMBOLS = [
     ("lk_index_destroy", c_int, [c_void_p]),
     ("lk_index_search", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int,
                                 c_int64, c_int, c_void_p]),
+    ("lk_index_check", c_int, [c_void_p]),
     ("lk_index_last_timing", c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     ("lk_index_set_timing", c_int, [c_void_p, c_int]),
     ("lk_index_storage_bytes", c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),

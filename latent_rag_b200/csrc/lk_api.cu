@@ -382,6 +382,19 @@ int lk_index_last_timing(lk_index* ix, float* out_search_kernel_ms, float* out_t
   return LK_OK;
 }
 
+int lk_index_check(lk_index* ix) {
+  if (!ix) return LK_ERR_INVALID;
+  DeviceGuard guard(ix->device);
+  int flag = 0;
+  LK_CUDA(cudaMemcpy(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));  // synchronises
+  if (flag != 0) {
+    cudaMemset(ix->err_flag, 0, sizeof(int));
+    set_error("search kernel pipeline timed out (barrier code %d); results are invalid", flag);
+    return LK_ERR_CUDA;
+  }
+  return LK_OK;
+}
+
 static int pick_kernel(const lk_index* ix, int requested, int k) {
   const char* env = getenv("LK_FORCE_KERNEL");
   if (env && !strcmp(env, "simt")) requested = LK_KERNEL_SIMT;

@@ -437,30 +437,21 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       // instruction cache): score every column and keep the running max.  Only when some
       // lane's max beats its k-th best does the warp take the slow path, which holds the
       // ONE copy of the insertion network and re-reads the candidate columns from TMEM.
-#pragma unroll 1
-      for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)(acc.idx * kUnitCols + ch * kColsPerWarp + chunk * 32);
-        ptx::tmem_ld32(taddr, r);
-        ptx::tmem_wait_ld();
-        if (p.debug_tile != nullptr && u == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ch == 0) p.debug_tile[lane_q * kBlockRows + chunk * 32 + j] = __uint_as_float(r[j]);
-        }
-        const float* sdc = sd + chunk * 32;
-        auto score = [&](float dot, float e_sd) -> float {
-          if (METRIC == LK_COSINE) return dot * e_sd;            // x 1/|e|; x 1/|q| at flush
-          return fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
-        };
-        float mg[4];  // running max per group of 8 columns (NaN never wins)
+      auto score = [&](float dot, float e_sd) -> float {
+        if (METRIC == LK_COSINE) return dot * e_sd;            // x 1/|e|; x 1/|q| at flush
+        return fmaf(2.0f, dot, -(q_sd + e_sd));                // -(|q|^2 + |e|^2 - 2 q.e)
+      };
+      // running max per group of 8 columns (NaN never wins)
+      auto group_max = [&](const uint32_t (&r)[32], const float* sdc, float (&mg)[4]) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           mg[g] = -INFINITY;
 #pragma unroll
           for (int j = 8 * g; j < 8 * g + 8; ++j) mg[g] = fmaxf(mg[g], score(__uint_as_float(r[j]), sdc[j]));
         }
+      };
+      // everything after the fast path of one chunk of 32 columns
+      auto select = [&](int chunk, uint32_t taddr, const uint32_t (&r)[32], const float* sdc, const float (&mg)[4]) {
         const float m = fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3]));
         if constexpr (SelectorFor<KSEL>::type::kAppend) {
           // k > 10: every lane appends its own hits (predicated, no divergence, no TMEM re-read),
@@ -482,23 +473,54 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
             thr = top.threshold();
           }
         } else if (__any_sync(0xffffffffu, m > thr)) {
-          unsigned pend = 0;
+          // k <= 10: only the 8-column groups in which some lane has a hit are looked at again
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            pend |= score(__uint_as_float(r[j]), sdc[j]) > thr ? (1u << j) : 0u;
-          unsigned umask = __reduce_or_sync(0xffffffffu, pend);
-          while (umask) {  // warp-uniform: one candidate column per turn
-            const int j = __ffs(umask) - 1;
-            umask &= umask - 1;
-            const float dot = __uint_as_float(ptx::tmem_ld1(taddr + (uint32_t)j));
-            ptx::tmem_wait_ld();
-            const float sc = score(dot, sdc[j]);
-            if (sc > thr) {  // rows arrive in ascending order: strict '>' keeps the lower index
-              top.insert(sc, row0 + chunk * 32 + j);
-              thr = top.threshold();
+          for (int g = 0; g < 4; ++g) {
+            if (!__any_sync(0xffffffffu, mg[g] > thr)) continue;
+            unsigned pend = 0;
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j)
+              pend |= score(__uint_as_float(r[j]), sdc[j]) > thr ? (1u << j) : 0u;
+            unsigned umask = __reduce_or_sync(0xffffffffu, pend);
+            while (umask) {  // warp-uniform: one candidate column per turn
+              const int j = __ffs(umask) - 1;
+              umask &= umask - 1;
+              const float dot = __uint_as_float(ptx::tmem_ld1(taddr + (uint32_t)j));
+              ptx::tmem_wait_ld();
+              const float sc = score(dot, sdc[j]);
+              if (sc > thr) {  // rows arrive in ascending order: strict '>' keeps the lower index
+                top.insert(sc, row0 + chunk * 32 + j);
+                thr = top.threshold();
+              }
             }
           }
         }
+      };
+      // Two chunks per turn: both tcgen05.ld are in flight together and the two independent
+      // score / max chains interleave, which hides most of the latency two warps per scheduler
+      // cannot; the selection steps then run in row order.
+#pragma unroll 1
+      for (int chunk = 0; chunk < kColsPerWarp / 32; chunk += 2) {
+        uint32_t r0[32], r1[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)(acc.idx * kUnitCols + ch * kColsPerWarp + chunk * 32);
+        ptx::tmem_ld32(taddr, r0);
+        ptx::tmem_ld32(taddr + 32u, r1);
+        ptx::tmem_wait_ld();
+        if (p.debug_tile != nullptr && u == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ch == 0) {
+              p.debug_tile[lane_q * kBlockRows + chunk * 32 + j] = __uint_as_float(r0[j]);
+              p.debug_tile[lane_q * kBlockRows + chunk * 32 + 32 + j] = __uint_as_float(r1[j]);
+            }
+        }
+        const float* sdc = sd + chunk * 32;
+        float mg0[4], mg1[4];
+        group_max(r0, sdc, mg0);
+        group_max(r1, sdc + 32, mg1);
+        select(chunk, taddr, r0, sdc, mg0);
+        select(chunk + 1, taddr + 32u, r1, sdc + 32, mg1);
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -252,6 +252,68 @@ __device__ __forceinline__ uint32_t buffer_shrink(float* bs, int32_t* bi, int n,
   return t;
 }
 
+// Whole warp: shrink the buffers of (at most `budget`) lanes holding more than `limit` entries, one
+// after the other, the next buffer's loads in flight while the current one is processed.
+// Returns this lane's (new count, new threshold bits).
+static __device__ __noinline__ uint2 buffer_compact_warp(float* bs, int32_t* bi, int cnt, float thr, float vmax, int k,
+                                                  int limit, int lane, uint64_t keep_policy, int budget) {
+  unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
+  __syncwarp();  // the appends of every lane are visible to the warp
+  auto ptr_s = [&](int src) {
+    return reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bs), src));
+  };
+  auto ptr_i = [&](int src) {
+    return reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bi), src));
+  };
+  uint32_t key[kBufPer], nkey[kBufPer];
+  int32_t id[kBufPer], nid[kBufPer];
+  int src = todo ? __ffs(todo) - 1 : -1;
+  todo &= todo - 1;
+  float* ps = nullptr;
+  int32_t* pi = nullptr;
+  int n = 0;
+  if (src >= 0) {
+    ps = ptr_s(src);
+    pi = ptr_i(src);
+    n = __shfl_sync(0xffffffffu, cnt, src);
+    buffer_load(ps, pi, n, lane, key, id);
+  }
+  while (src >= 0) {
+    int nsrc = -1, nn = 0;
+    float* nps = nullptr;
+    int32_t* npi = nullptr;
+    if (todo && --budget > 0) {
+      nsrc = __ffs(todo) - 1;
+      todo &= todo - 1;
+      nps = ptr_s(nsrc);
+      npi = ptr_i(nsrc);
+      nn = __shfl_sync(0xffffffffu, cnt, nsrc);
+      buffer_load(nps, npi, nn, lane, nkey, nid);
+    }
+    const float t_old = __shfl_sync(0xffffffffu, thr, src);
+    const uint32_t lo = t_old > -INFINITY ? order_key(t_old) : 0x007fffffu;
+    const uint32_t hi = order_key(__shfl_sync(0xffffffffu, vmax, src));
+    const int kk = __shfl_sync(0xffffffffu, k, src);
+    int kept;
+    const uint32_t t = buffer_shrink(ps, pi, n, kk, lo, hi, lane, keep_policy, key, id, &kept);
+    if (lane == src) {
+      cnt = kept;
+      thr = order_key_inv(t);
+    }
+    src = nsrc;
+    ps = nps;
+    pi = npi;
+    n = nn;
+#pragma unroll
+    for (int j = 0; j < kBufPer; ++j) {
+      key[j] = nkey[j];
+      id[j] = nid[j];
+    }
+  }
+  __syncwarp();
+  return make_uint2((unsigned)cnt, __float_as_uint(thr));
+}
+
 struct BufSelector {
   static constexpr bool kAppend = true;
   float* bs;
@@ -277,59 +339,14 @@ struct BufSelector {
     ptx::st_hint(bi + cnt, id, keep_policy);
     ++cnt;
   }
-  // Whole warp: shrink the buffers of (at most `budget`) lanes holding more than `limit` entries,
-  // one after the other, the next buffer's loads in flight while the current one is processed.
+  // Whole warp: shrink the buffers of (at most `budget`) lanes holding more than `limit` entries.
+  // The work is in a non-inlined function (it is large and rare; the epilogue loop that calls it
+  // from several places has to stay inside the instruction cache).
   __device__ __forceinline__ void compact(int limit, int lane, uint64_t keep_policy, int budget = 32) {
-    unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
-    if (!todo) return;
-    __syncwarp();  // the appends of every lane are visible to the warp
-    auto ptr_s = [&](int src) {
-      return reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bs), src));
-    };
-    auto ptr_i = [&](int src) {
-      return reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(bi), src));
-    };
-    uint32_t key[kBufPer], nkey[kBufPer];
-    int32_t id[kBufPer], nid[kBufPer];
-    int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    float* ps = ptr_s(src);
-    int32_t* pi = ptr_i(src);
-    int n = __shfl_sync(0xffffffffu, cnt, src);
-    buffer_load(ps, pi, n, lane, key, id);
-    while (src >= 0) {
-      int nsrc = -1, nn = 0;
-      float* nps = nullptr;
-      int32_t* npi = nullptr;
-      if (todo && --budget > 0) {
-        nsrc = __ffs(todo) - 1;
-        todo &= todo - 1;
-        nps = ptr_s(nsrc);
-        npi = ptr_i(nsrc);
-        nn = __shfl_sync(0xffffffffu, cnt, nsrc);
-        buffer_load(nps, npi, nn, lane, nkey, nid);
-      }
-      const float t_old = __shfl_sync(0xffffffffu, thr, src);
-      const uint32_t lo = t_old > -INFINITY ? order_key(t_old) : 0x007fffffu;
-      const uint32_t hi = order_key(__shfl_sync(0xffffffffu, vmax, src));
-      const int kk = __shfl_sync(0xffffffffu, k, src);
-      int kept;
-      const uint32_t t = buffer_shrink(ps, pi, n, kk, lo, hi, lane, keep_policy, key, id, &kept);
-      if (lane == src) {
-        cnt = kept;
-        thr = order_key_inv(t);
-      }
-      src = nsrc;
-      ps = nps;
-      pi = npi;
-      n = nn;
-#pragma unroll
-      for (int j = 0; j < kBufPer; ++j) {
-        key[j] = nkey[j];
-        id[j] = nid[j];
-      }
-    }
-    __syncwarp();
+    if (!__any_sync(0xffffffffu, cnt > limit)) return;
+    const uint2 res = buffer_compact_warp(bs, bi, cnt, thr, vmax, k, limit, lane, keep_policy, budget);
+    cnt = (int)res.x;
+    thr = __uint_as_float(res.y);
   }
   // Leaves the best entries seen (at least min(k, seen) of them, unordered, at most kBufCap) in
   // slots [0, cnt); the merge kernel does the final selection.

@@ -164,6 +164,10 @@ class ExactIndex:
             return d, i
         return d.numpy().copy(), i.numpy().copy()
 
+    def check(self) -> None:
+        """Synchronise and raise if a search with device outputs hit a pipeline timeout."""
+        nat.check(self._lib.lk_index_check(self._h), "lk_index_check")
+
     # -- persistence ------------------------------------------------------------------
     def export_bytes(self) -> Tuple[np.ndarray, np.ndarray]:
         tb, sb = c_int64(0), c_int64(0)

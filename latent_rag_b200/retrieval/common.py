@@ -116,5 +116,6 @@ class BatchedRetrieveMixin:
                                        c_void_p(int(torch.cuda.current_stream(dev).cuda_stream))),
                   "lk_maxsim_rerank")
         ids, sc = out_d.cpu().numpy(), out_s.cpu().numpy()
+        self.index.check()
         keep = np.isfinite(sc)  # padding: fewer documents than top_k among the candidates
         return ([ids[r][keep[r]].tolist() for r in range(b)], [sc[r][keep[r]].tolist() for r in range(b)])

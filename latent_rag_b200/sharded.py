@@ -133,6 +133,8 @@ class ShardedRetriever:
         out_d, out_i = self.search_tensors(queries, k)
         if torch.is_tensor(out_d):
             out_d, out_i = out_d.cpu().numpy(), out_i.cpu().numpy()
+        if self.index is not None:
+            self.index.check()  # device-output searches do not synchronise by themselves
         if self._xchg is not None:
             self._xchg.check()  # a peer that never published shows up here, not as a hang
         b = 1 if queries.dim() == 1 else queries.size(0)

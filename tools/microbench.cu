@@ -120,6 +120,48 @@ __global__ void __launch_bounds__(128) mma_rate(int n_cols, int layout, int iter
   }
 }
 
+// ---- 4. TMEM read rate: tcgen05.ld.32x32b.x32 from n_warps warps, `depth` loads in flight per warp
+__global__ void __launch_bounds__(512) tmem_read_rate(int n_warps, int depth, int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_ptr;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_ptr), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_ptr;
+  float acc = 0.f;
+  long long t0 = 0, t1 = 0;
+  if (warp < n_warps) {
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t r0[32], r1[32];
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t col = (uint32_t)(((it * 2 + (warp >> 2)) * 32) & 511);
+      ptx::tmem_ld32(tmem + lane_base + col, r0);
+      if (depth == 2) ptx::tmem_ld32(tmem + lane_base + ((col + 256) & 511), r1);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r0[j]));
+      if (depth == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaxf(acc, __uint_as_float(r1[j]));
+      }
+    }
+    t1 = clock64();
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+  if (acc == 12345.f) sink[0] = acc;
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 512);
+  }
+}
+
 int main() {
   int dev = 0;
   cudaDeviceProp prop;
@@ -196,6 +238,25 @@ int main() {
                (double)h / (iters * 4), herr);
       }
     }
+  }
+  {
+    long long* cyc;
+    float* sink;
+    CK(cudaMalloc(&cyc, 8));
+    CK(cudaMalloc(&sink, 4));
+    for (int depth : {1, 2})
+      for (int nw : {1, 4, 8, 12, 16}) {
+        const int iters = 4000;
+        for (int rep = 0; rep < 2; ++rep) {
+          tmem_read_rate<<<sms, 512>>>(nw, depth, iters, cyc, sink);
+          CK(cudaDeviceSynchronize());
+        }
+        long long h = 0;
+        CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+        const double loads = (double)iters * depth;  // per warp; each moves 32 lanes x 32 cols x 4 B = 4 KB
+        printf("tcgen05.ld.32x32b.x32 %2d warps, %d in flight: %.1f cycles per load per warp, %.1f B/cycle/SM\n", nw,
+               depth, (double)h / loads, 4096.0 * loads * nw / (double)h);
+      }
   }
   return 0;
 }
