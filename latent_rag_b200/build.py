@@ -56,7 +56,8 @@ def _headers() -> List[str]:
 
 
 def _compile(nvcc: str, src: str, obj: str, log_dir: str) -> str:
-    cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+    extra = os.environ.get("LK_NVCC_EXTRA", "").split()  # experiments, e.g. -DLK_EPI_WARPS=16
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     with open(os.path.join(log_dir, os.path.basename(src) + ".ptxas.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
