@@ -131,6 +131,18 @@ int lk_maxsim_rerank(int device, const float* cand_scores, const int64_t* cand_i
                      const int64_t* row_doc_ids, int64_t n_rows, int top_k, float* out_scores,
                      int64_t* out_doc_ids, void* stream);
 
+/* ---- retrieval metrics per query: replaces recall_at_k / mrr / ndcg_at_k
+ *      (evaluation/retrieval_metrics.py:14-31) under evaluate_retrieval (:55-96, main.py:321).
+ *      retrieved: n_queries x n_retrieved ids (< 0 = padding of a shorter list); the relevant ids of
+ *      query q are rel_ids[rel_offsets[q] .. rel_offsets[q+1]); metric m is metric_kind[m]
+ *      (0 recall, 1 mrr, 2 ndcg) at cut-off metric_k[m] (<= 0: the whole list); discounts[i] =
+ *      1 / log2(i + 2) in float64; out: n_queries x n_metrics float64.  All pointers are device
+ *      memory.  The values equal the reference's bit for bit (same float64 sums, left to right). */
+int lk_retrieval_metrics(int device, const int64_t* retrieved, int64_t n_queries, int n_retrieved,
+                         const int64_t* rel_offsets, const int64_t* rel_ids, const int* metric_kind,
+                         const int* metric_k, int n_metrics, const double* discounts, double* out,
+                         void* stream);
+
 /* ---- candidate exchange between the GPUs of a row-sharded index, fused with that merge
  *      (net-new).  One process per GPU.  Every rank owns a symmetric
  *      buffer; the peers' buffers are mapped through CUDA IPC (the handles travel over the

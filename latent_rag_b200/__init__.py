@@ -10,9 +10,10 @@ from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, Variati
                            load_autoencoder)
 from .sharded import ShardedRetriever, shard_bounds
 from .exchange import PeerExchange
+from .evaluation import evaluate_retrieval
 
 __all__ = [
     "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
-    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval",
 ]

@@ -446,6 +446,42 @@ def test_retrieve_batch_equals_the_per_query_loop(lrb, cls):
 
 
 # ---------------------------------------------------------------------------------------
+# retrieval metrics on the device (evaluation/retrieval_metrics.py:14-96)
+# ---------------------------------------------------------------------------------------
+def test_device_metrics_equal_the_reference_bit_for_bit(lrb, golden):
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "metrics_golden.json")) as f:
+        g = json.load(f)
+    # the KATs of test/test_evaluation.py:9-22, through the single-query form
+    one = lrb.evaluate_retrieval([1, 2, 3, 4, 5], [3, 4, 6], ["recall@3", "mrr", "ndcg@3"])
+    assert one["recall@3"] == 1 / 3 == g["kat"]["recall_at_3"]
+    assert one["mrr"] == 1 / 3 == g["kat"]["mrr"]
+    assert one["ndcg@3"] == g["kat"]["ndcg_at_3"]
+    # the seeded batch whose summary the reference produced (tests/golden/make_golden.py::metrics)
+    retrieved, relevant = inputs.metrics_case()
+    names = list(g["evaluate_retrieval"])
+    res, per_query = lrb.evaluate_retrieval(retrieved, relevant, names, return_per_query=True)
+    for name, ref in g["evaluate_retrieval"].items():
+        assert res[name]["mean"] == ref["mean"] and res[name]["std"] == ref["std"], name
+    # ragged lists, duplicates, empty relevant sets, string ids: against the oracle, per query
+    rng = np.random.default_rng(8)
+    ret = [[f"d{v}" for v in rng.integers(0, 30, int(rng.integers(1, 40)))] for _ in range(300)]
+    rel = [[f"d{v}" for v in rng.integers(0, 30, int(rng.integers(0, 5)))] for _ in range(300)]
+    names = ["Recall@10", "MRR@10", "nDCG@10", "recall@3", "mrr", "ndcg@50"]
+    res, per_query = lrb.evaluate_retrieval(ret, rel, names, return_per_query=True)
+    want = oracle.evaluate_retrieval(ret, rel, names)
+    for n in names:
+        assert abs(res[n]["mean"] - want[n]["mean"]) < 1e-15 and abs(res[n]["std"] - want[n]["std"]) < 1e-15
+    for r, l, pq in zip(ret, rel, per_query):
+        assert pq["Recall@10"] == oracle.recall_at_k(r, l, 10)
+        assert pq["MRR@10"] == oracle.mrr(r[:10], l)
+        assert abs(pq["nDCG@10"] - oracle.ndcg_at_k(r, l, 10)) < 1e-15
+    with pytest.raises(ValueError):
+        lrb.evaluate_retrieval(ret, rel, ["precision@5"])
+
+
+# ---------------------------------------------------------------------------------------
 # merge kernel + sharding
 # ---------------------------------------------------------------------------------------
 def test_merge_kernel_matches_oracle(lrb):
