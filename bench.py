@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--batch1-steps", type=int, default=20)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU candidate exchange: fused peer-to-peer kernel, or NCCL all-gather + merge")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=256)
     return ap.parse_args()
@@ -148,7 +150,9 @@ def workload_config(args, world):
         "workload": f"config 5: cosine top-{args.k} over {args.rows} x {args.dim} bf16 rows, "
                     f"{args.batch}-query batches (+ batch-1 sweep point), row-sharded over {world} GPU(s)",
         "rows": args.rows, "dim": args.dim, "batch": args.batch, "k": args.k, "rows_per_gpu": -(-args.rows // world),
-        "parallelism": f"row-shard x{world} + all-gather k-merge",
+        "parallelism": (f"row-shard x{world} + candidate exchange fused with the k-merge "
+                        f"({'peer-to-peer stores over NVLink' if args.exchange == 'p2p' else 'NCCL all-gather'})"
+                        if world > 1 else "one GPU holds the whole corpus"),
         "l2": "inputs larger than L2 (each rank streams its whole corpus shard every step)",
     }
 
@@ -232,10 +236,18 @@ def main():
     q_dev = q_host.to(dev)
     k = args.k
 
+    xchg = None
+    if world > 1 and args.exchange == "p2p":
+        xchg = lrb.PeerExchange(local_rank, rank, world, max_b=max(args.batch, 1)).connect()
+
     def gather_merge(d, i):
-        """all-gather of the [B,k] candidates + merge kernel (the one exchange step)."""
+        """The one exchange step: the [B,k] candidates of every rank -> the global top-k on every
+        rank.  p2p: one kernel per rank (stores into every peer's buffer over NVLink, flags, wait,
+        merge); nccl: all-gather + merge kernel."""
         if world == 1:
             return d, i
+        if xchg is not None:
+            return xchg.exchange_merge(d, i, k)
         b = d.size(0)
         gd = torch.empty((world * b, k), dtype=torch.float32, device=dev)
         gi = torch.empty((world * b, k), dtype=torch.int64, device=dev)
@@ -310,6 +322,9 @@ def main():
     kms1 = kernel_ms(q1_dev, args.batch1_steps)
 
     # ---- full-size correctness properties (outside the timed regions) -----------------
+    index.check()  # no search kernel hit a pipeline timeout
+    if xchg is not None:
+        xchg.check()  # no rank timed out waiting for a peer's candidates
     d_fin, i_fin = out[0].cpu().numpy(), out[1].cpu().numpy()
     planted_ok = bool((i_fin[qpos, 0] == planted).all())
     sorted_ok = bool((np.diff(d_fin, axis=1) <= 0).all())
