@@ -143,6 +143,13 @@ int lk_retrieval_metrics(int device, const int64_t* retrieved, int64_t n_queries
                          const int* metric_k, int n_metrics, const double* discounts, double* out,
                          void* stream);
 
+/* ---- 1-based rank of every query's paired document among all documents by cosine similarity:
+ *      replaces _rank_positive (evaluation/embedding_visualization.py:34-37), which broadcasts an
+ *      [n, n, D] tensor and argsorts twice.  queries, docs: n x dim fp32 row-major, device memory;
+ *      out_rank: n int64, device.  rank = 1 + #{j != i : cos(q_i, d_j) > cos(q_i, d_i)}. */
+int lk_rank_positive(int device, const float* queries, const float* docs, int64_t n, int dim,
+                     int64_t* out_rank, void* stream);
+
 /* ---- candidate exchange between the GPUs of a row-sharded index, fused with that merge
  *      (net-new).  One process per GPU.  Every rank owns a symmetric
  *      buffer; the peers' buffers are mapped through CUDA IPC (the handles travel over the

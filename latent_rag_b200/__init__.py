@@ -10,10 +10,10 @@ from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, Variati
                            load_autoencoder)
 from .sharded import ShardedRetriever, shard_bounds
 from .exchange import PeerExchange
-from .evaluation import evaluate_retrieval
+from .evaluation import evaluate_retrieval, rank_positive
 
 __all__ = [
     "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
-    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval", "rank_positive",
 ]

@@ -55,6 +55,7 @@ SYMBOLS = [
                                  c_void_p, c_void_p]),
     ("lk_retrieval_metrics", c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                      c_void_p, c_void_p, c_void_p]),
+    ("lk_rank_positive", c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     ("lk_comm_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int64, c_int]),
     ("lk_comm_ipc_handle", c_int, [c_void_p, c_void_p]),
     ("lk_comm_open_peers", c_int, [c_void_p, c_void_p]),

@@ -69,10 +69,94 @@ __global__ void __launch_bounds__(kMetricWarps * 32) retrieval_metrics_kernel(
   }
 }
 
+// ---- all-pairs rank of the paired ("positive") document, evaluation/embedding_visualization.py:34-37:
+//      sim = cosine_similarity(q[:, None], d[None, :]); rank_i = 1 + #{j : sim[i, j] > sim[i, i]}
+//      (the reference materialises the [n, n, D] broadcast and argsorts twice).  fp32 like the
+//      reference: rows normalised as x / max(|x|, 1e-8), one CTA per query, one warp per document.
+constexpr int kRankThreads = 256;
+
+__global__ void __launch_bounds__(kRankThreads) rank_positive_kernel(const float* __restrict__ q,
+                                                                     const float* __restrict__ d, int64_t n, int dim,
+                                                                     int64_t* __restrict__ out_rank) {
+  extern __shared__ float s_q[];  // the normalised query
+  __shared__ float s_red[kRankThreads / 32];
+  __shared__ float s_self;
+  __shared__ int s_count;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i = blockIdx.x;
+  float ss = 0.f;
+  for (int k = tid; k < dim; k += kRankThreads) {
+    const float v = q[i * dim + k];
+    s_q[k] = v;
+    ss = fmaf(v, v, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) s_red[warp] = ss;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < kRankThreads / 32; ++w) tot += s_red[w];
+  const float q_inv = 1.0f / fmaxf(sqrtf(tot), 1e-8f);
+  auto cosine = [&](int64_t j) -> float {  // whole warp; every lane returns the value
+    const float* dj = d + j * dim;
+    float dot = 0.f, d2 = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float v = dj[k];
+      dot = fmaf(s_q[k] * q_inv, v, dot);
+      d2 = fmaf(v, v, d2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    return dot / fmaxf(sqrtf(d2), 1e-8f);
+  };
+  if (warp == 0) {
+    const float self = cosine(i);
+    if (lane == 0) s_self = self;
+  }
+  __syncthreads();
+  const float self = s_self;
+  int cnt = 0;
+  for (int64_t j = warp; j < n; j += kRankThreads / 32)
+    if (j != i) cnt += cosine(j) > self ? 1 : 0;
+  if (lane == 0 && cnt) atomicAdd(&s_count, cnt);
+  __syncthreads();
+  if (tid == 0) out_rank[i] = (int64_t)s_count + 1;
+}
+
 }  // namespace
 }  // namespace lk
 
 using namespace lk;
+
+extern "C" int lk_rank_positive(int device, const float* queries, const float* docs, int64_t n, int dim,
+                                int64_t* out_rank, void* stream) {
+  if (n < 0 || dim < 1 || dim > 8192 || (n > 0 && (!queries || !docs || !out_rank))) {
+    set_error("lk_rank_positive: bad argument");
+    return LK_ERR_INVALID;
+  }
+  if (n == 0) return LK_OK;
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+  if (device < 0 || device >= cnt) {
+    set_error("device %d out of range (%d visible)", device, cnt);
+    return LK_ERR_INVALID;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  LK_CUDA(cudaSetDevice(device));
+  rank_positive_kernel<<<(unsigned)n, kRankThreads, (size_t)dim * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      queries, docs, n, dim, out_rank);
+  cudaError_t le = cudaGetLastError();
+  if (prev >= 0) cudaSetDevice(prev);
+  count_launch();
+  if (le != cudaSuccess) return cuda_fail(le, "rank_positive_kernel", __FILE__, __LINE__);
+  return LK_OK;
+}
 
 extern "C" int lk_retrieval_metrics(int device, const int64_t* retrieved, int64_t n_queries, int n_retrieved,
                                     const int64_t* rel_offsets, const int64_t* rel_ids, const int* metric_kind,

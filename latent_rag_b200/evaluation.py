@@ -94,3 +94,23 @@ def evaluate_retrieval(retrieved_batch, relevant_batch, metrics: Optional[List[s
     if single:
         return {k: v["mean"] for k, v in summary.items()}
     return summary
+
+
+def rank_positive(q: torch.Tensor, d: torch.Tensor, device: Optional[int] = None) -> torch.Tensor:
+    """1-based rank of each query's paired document by cosine similarity: drop-in for
+    `_rank_positive` of the reference (evaluation/embedding_visualization.py:34-37), without
+    the [n, n, D] broadcast.  Returns an int64 tensor on the device of `q`."""
+    if q.dim() != 2 or q.shape != d.shape:
+        raise ValueError(f"expected two [n, D] tensors of the same shape, got {tuple(q.shape)} and {tuple(d.shape)}")
+    lib = nat.load()
+    nat.require_device()
+    if device is None:
+        device = q.device.index if q.is_cuda else torch.cuda.current_device()
+    dev = torch.device(f"cuda:{device}")
+    qd = q.detach().to(dev, torch.float32).contiguous()
+    dd = d.detach().to(dev, torch.float32).contiguous()
+    out = torch.empty(q.size(0), dtype=torch.int64, device=dev)
+    nat.check(lib.lk_rank_positive(device, c_void_p(qd.data_ptr()), c_void_p(dd.data_ptr()), q.size(0), q.size(1),
+                                   c_void_p(out.data_ptr()),
+                                   c_void_p(int(torch.cuda.current_stream(device).cuda_stream))), "lk_rank_positive")
+    return out if q.is_cuda else out.cpu()

@@ -82,3 +82,16 @@ def maxsim_rerank(scores_k, docids_k, top_k: int):
             agg[did] = sc
     ranked = sorted(agg, key=agg.get, reverse=True)[:top_k]
     return ranked, [agg[d] for d in ranked]
+
+
+def rank_positive(q, d):
+    """1-based rank of each paired document by cosine similarity
+    (evaluation/embedding_visualization.py:34-37): rank_i = 1 + #{j : sim[i, j] > sim[i, i]}
+    (equal to the reference's double argsort whenever no other document ties with the pair)."""
+    import torch
+    import torch.nn.functional as F
+
+    qn = F.normalize(q.detach().to("cpu", torch.float32), dim=-1, eps=1e-8)
+    dn = F.normalize(d.detach().to("cpu", torch.float32), dim=-1, eps=1e-8)
+    sim = qn @ dn.T
+    return (sim > sim.diagonal().unsqueeze(1)).sum(dim=1) + 1

@@ -74,3 +74,12 @@ def maxsim_case(q: int = 30, ck: int = 30, docs: int = 12, seed: int = 91):
     did = rng.integers(0, docs, size=(q, ck)).astype(np.int64)
     did[1] = np.arange(ck) % 3  # only three documents among the candidates: fewer than top_k
     return sc, did
+
+
+def rank_case(n: int = 200, d: int = 32, seed: int = 17):
+    """Paired (query, document) embeddings for the positive-rank helper
+    (evaluation/embedding_visualization.py:34-37): documents are noisy copies of the queries."""
+    rng = np.random.default_rng(seed)
+    q = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
+    noise = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
+    return q, q + 1.5 * noise

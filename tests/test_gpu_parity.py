@@ -481,6 +481,21 @@ def test_device_metrics_equal_the_reference_bit_for_bit(lrb, golden):
         lrb.evaluate_retrieval(ret, rel, ["precision@5"])
 
 
+def test_rank_positive_matches_reference_outputs(lrb):
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "rank_golden.json")) as f:
+        gold = json.load(f)["ranks"]
+    q, d = inputs.rank_case()
+    assert lrb.rank_positive(q, d).tolist() == gold
+    assert lrb.rank_positive(q.cuda(), d.cuda()).is_cuda
+    rng = np.random.default_rng(3)
+    q2 = torch.from_numpy(rng.standard_normal((3000, 384)).astype(np.float32))
+    d2 = q2 + 2.0 * torch.from_numpy(rng.standard_normal((3000, 384)).astype(np.float32))
+    got, want = lrb.rank_positive(q2, d2), oracle.rank_positive(q2, d2)
+    assert (got - want).abs().max().item() <= 1 and (got != want).float().mean().item() < 0.01  # fp32 near-ties
+
+
 # ---------------------------------------------------------------------------------------
 # merge kernel + sharding
 # ---------------------------------------------------------------------------------------

@@ -156,3 +156,13 @@ def test_oracle_maxsim_matches_reference_outputs():
         ranked, scores = oracle.maxsim_rerank(sc[g["row"]].tolist(), did[g["row"]].tolist(), g["top_k"])
         assert ranked == g["ranked_docids"]
         assert scores == sorted(scores, reverse=True)
+
+
+def test_oracle_rank_positive_matches_reference_outputs():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "rank_golden.json")) as f:
+        gold = json.load(f)["ranks"]
+    q, d = inputs.rank_case()
+    assert oracle.rank_positive(q, d).tolist() == gold
