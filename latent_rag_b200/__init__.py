@@ -5,7 +5,8 @@ torch.distributed.  No CPU fallback."""
 from . import _native
 from ._native import NativeError
 from .engine import ExactIndex, merge_topk
-from .retrieval import BruteForceRetriever, FAISSEmbeddingRetriever, StatsTracker, build_retriever
+from .retrieval import (BruteForceRetriever, EmbeddingCompressor, FAISSEmbeddingRetriever, StatsTracker,
+                        build_retriever)
 from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, VariationalAutoencoder,
                            load_autoencoder)
 from .sharded import ShardedRetriever, shard_bounds
@@ -13,7 +14,7 @@ from .exchange import PeerExchange
 from .evaluation import evaluate_retrieval, rank_positive
 
 __all__ = [
-    "ExactIndex", "merge_topk", "BruteForceRetriever", "FAISSEmbeddingRetriever", "StatsTracker",
+    "ExactIndex", "merge_topk", "BruteForceRetriever", "EmbeddingCompressor", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
     "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval", "rank_positive",
 ]

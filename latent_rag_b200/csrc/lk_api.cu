@@ -438,7 +438,8 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   const size_t qt_bytes = (size_t)(b_pad / kBlockRows) * ix->g.block_bytes();
   if ((rc = ix->q_tiles.ensure(qt_bytes)) != LK_OK) return rc;
   if ((rc = ix->q_side.ensure((size_t)b_pad * sizeof(float))) != LK_OK) return rc;
-  LK_CUDA(cudaMemsetAsync(ix->q_tiles.p, 0, qt_bytes, st));
+  // no clearing: padded query rows only feed accumulator lanes nobody reads, and the K padding of
+  // the real rows is written by the tiling kernel
   rc = ingest_rows(ix, queries, q_dtype, q_mem, b, ix->q_tiles.p, ix->q_side.as<float>(), 0, st);
   if (rc != LK_OK) return rc;
 
@@ -498,17 +499,14 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
 
   // 3. fused distance + selection
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
-  if (seed_rows > 0) {
-    LK_CUDA(cudaMemsetAsync(a0.part_cnt, 0, n_cnt0 * sizeof(int), st));  // lists are read up to their count
+  if (seed_rows > 0) {  // (the tcgen05 kernel marks the list slots it does not own itself)
     if ((rc = launch_search_umma(a0, ix->sm_count, st)) != LK_OK) return rc;
     rc = launch_merge_i32(a0.part_scores, a0.part_idx, a0.part_cnt, b, a0.n_lists, merge_len, a0.ksel, k, 0, d_s,
                           d_i, st);
     if (rc != LK_OK) return rc;
     a.seed = d_s;  // read at the start of the main kernel's segments, overwritten by the final merge
   }
-  if (counted) {
-    LK_CUDA(cudaMemsetAsync(a.part_cnt, 0, n_cnt * sizeof(int), st));
-  } else {
+  if (which != LK_KERNEL_UMMA) {
     LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
     LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
   }

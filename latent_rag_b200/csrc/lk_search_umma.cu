@@ -545,6 +545,24 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         top.finish(q_sd, METRIC == LK_COSINE, p.k, lane);  // cosine: x 1/|q| once per kept entry
         if constexpr (SelectorFor<KSEL>::type::kAppend)
           if (cnt_out != nullptr) *cnt_out = top.cnt;
+        // The partial-list arrays are not cleared before the launch: the last group of a query
+        // tile marks the list slots no group owns (n_lists is the maximum over query tiles).
+        {
+          const int64_t qg = qt / CG;
+          const int64_t c_first = cta_of_unit(qg * p.nblk, p.total_units, G);
+          const int64_t c_last = cta_of_unit((qg + 1) * p.nblk - 1, p.total_units, G);
+          const int64_t q = (int64_t)qt * kBlockRows + lane_q;
+          if (c == c_last && q < p.n_queries) {
+            for (int l = (int)(c - c_first + 1) * kColSplit + ch; l < p.n_lists; l += kColSplit) {
+              if constexpr (SelectorFor<KSEL>::type::kAppend) {
+                p.part_cnt[q * p.n_lists + l] = 0;
+              } else {
+                int32_t* e = p.part_idx + (q * p.n_lists + l) * p.ksel;
+                for (int j = 0; j < p.ksel; ++j) e[j] = -1;
+              }
+            }
+          }
+        }
         seg_start = true;
       }
       b = nb;

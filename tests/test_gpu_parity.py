@@ -373,6 +373,30 @@ def test_ae_tensor_core_kernel_is_rejected_for_unsupported_dims(lrb):
         ae.encode(torch.zeros(300, 16))
 
 
+def test_embedding_compressor_contract(lrb):
+    """retrieval/embedder.py:24-48 with a stand-in sentence encoder (the SBERT forward is out of
+    scope): normalised base embeddings -> fused encoder -> float32 CPU tensor; VAE -> mu."""
+    class FakeSbert:
+        def encode(self, texts, batch_size=64, convert_to_tensor=True, normalize_embeddings=True):
+            g = torch.Generator().manual_seed(len(texts))
+            x = torch.randn((len(texts), 384), generator=g)
+            return x / x.norm(dim=1, keepdim=True) if normalize_embeddings else x
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    texts = [f"t{i}" for i in range(300)]
+    base = FakeSbert().encode(texts)
+    for kind in ("vae", "cae"):
+        ae = lrb.load_autoencoder(kind, os.path.join(gold, f"ae_weights_{kind}.npz"))
+        comp = lrb.EmbeddingCompressor(autoencoder=ae, device="cuda:0", model=FakeSbert())
+        z = comp.encode_text(texts)
+        assert z.shape == (300, 64) and z.dtype == torch.float32 and not z.is_cuda
+        w = oracle.load_encoder_weights(np.load(os.path.join(gold, f"ae_weights_{kind}.npz")), kind)
+        ref = oracle.ae_encode(base, w, kind)
+        assert ((z - ref).abs() / ref.abs().amax(dim=1, keepdim=True)).max().item() < 3e-5
+        raw = comp.encode_text(texts, compress=False)
+        assert raw.shape == (300, 384) and torch.equal(raw, base)
+
+
 def test_latent_pipeline_config2_shape(lrb):
     """config 2 in miniature: encode corpus + queries with the shipped CAE, cosine top-10."""
     gold = os.path.join(os.path.dirname(__file__), "golden")
