@@ -191,6 +191,11 @@ int lk_ae_create(lk_ae** out, int device, int kind, int d_in, int d_hidden, int 
  * reference's arithmetic); LK_KERNEL_AUTO (default): UMMA for calls of >= 256 rows when
  * available, SIMT otherwise. */
 int lk_ae_set_kernel(lk_ae* ae, int kernel);
+/* Operand precision of the tensor-core kernel.  LK_F32 (default): split-bf16 operands, fp32-level
+ * results.  LK_BF16: inputs, weights and hidden activations rounded to bf16 once, one MMA per
+ * product, fp32 accumulate (the same stated precision as the bf16 search): ~2x faster, and the
+ * latents are stored in bf16 by the search index anyway.  Implies the tensor-core kernel. */
+int lk_ae_set_precision(lk_ae* ae, int precision);
 /* x: m x d_in fp32 row-major; z: m x d_latent fp32 row-major */
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream);
 int lk_ae_destroy(lk_ae* ae);

@@ -49,6 +49,7 @@ SYMBOLS = [
     ("lk_ae_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p]),
     ("lk_ae_set_kernel", c_int, [c_void_p, c_int]),
+    ("lk_ae_set_precision", c_int, [c_void_p, c_int]),
     ("lk_ae_encode", c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p]),
     ("lk_ae_destroy", c_int, [c_void_p]),
     ("lk_maxsim_rerank", c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p,

@@ -34,6 +34,7 @@ class _FusedEncoder:
         self._lib = None
         self._weights: Optional[Dict[str, np.ndarray]] = None
         self._kernel = "auto"
+        self._precision = "fp32"
         self.training = False
 
     # -- nn.Module-shaped surface used by the reference pipeline -----------------------
@@ -78,6 +79,17 @@ class _FusedEncoder:
             nat.check(self._lib.lk_ae_set_kernel(self._h, nat.KERNELS[kernel]), "lk_ae_set_kernel")
         return self
 
+    def set_precision(self, precision: str):
+        """"fp32" (default): fp32-level results on every kernel.  "bf16": inputs, weights and hidden
+        activations rounded to bf16, fp32 accumulate, on the tensor-core kernel (about twice as fast;
+        the search index stores the latents in bf16 anyway)."""
+        if precision not in nat.STORAGE:
+            raise ValueError(f"Unknown precision: {precision}")
+        self._precision = precision
+        if self._h:
+            nat.check(self._lib.lk_ae_set_precision(self._h, nat.STORAGE[precision]), "lk_ae_set_precision")
+        return self
+
     # -- native handle -------------------------------------------------------------------
     def _release(self):
         if self._h:
@@ -108,6 +120,8 @@ class _FusedEncoder:
         )
         if self._kernel != "auto":
             nat.check(self._lib.lk_ae_set_kernel(self._h, nat.KERNELS[self._kernel]), "lk_ae_set_kernel")
+        if self._precision != "fp32":
+            nat.check(self._lib.lk_ae_set_precision(self._h, nat.STORAGE[self._precision]), "lk_ae_set_precision")
         return self._h
 
     def _encode(self, x: torch.Tensor) -> torch.Tensor:

@@ -49,6 +49,7 @@ struct AeParams {
   float* z;                       // [m, n1_true]
   int64_t m;
   int n_tiles, nkb0, n_chunks, n1, n1_true, l2norm;
+  int np;                         // operand planes in use: 2 = split-bf16 (hi + lo, three MMAs per product), 1 = plain bf16
   int* err_flag;
 };
 
@@ -134,9 +135,10 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
           if (!wait(empty_bar(st.idx), st.phase ^ 1u)) { fail(kAeProd); ok = false; break; }
           if (ptx::elect_one()) {
             const uint32_t dst = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
-            ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
+            ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)(2 * p.np * kSlabBytes));
 #pragma unroll
             for (int pl = 0; pl < kPlanes; ++pl) {
+              if (pl >= p.np) break;
               ptx::bulk_g2s(dst + pl * kSlabBytes, xt + ((int64_t)pl * p.nkb0 + kb) * kSlabBytes, kSlabBytes,
                             full_bar(st.idx));
               ptx::bulk_g2s(dst + (kPlanes + pl) * kSlabBytes, wc + ((int64_t)pl * p.nkb0 + kb) * kSlabBytes,
@@ -150,12 +152,13 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
         // W1 slabs of this hidden chunk (K blocks 2c, 2c+1 of layer 1), both planes
         if (!wait(w1empty_bar, (w1_uses & 1u) ^ 1u)) { fail(kAeProdW1); ok = false; break; }
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(w1full_bar, (uint32_t)(kPlanes * 2 * w1_slab));
+          ptx::mbar_arrive_expect_tx(w1full_bar, (uint32_t)(p.np * 2 * w1_slab));
           const int nkb1 = 2 * p.n_chunks;
 #pragma unroll
           for (int pl = 0; pl < kPlanes; ++pl)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
+              if (pl < p.np)
               ptx::bulk_g2s(ptx::smem_u32(w1_sm + (pl * 2 + j) * w1_slab),
                             p.w1_slabs + ((int64_t)pl * nkb1 + 2 * c + j) * w1_slab, (uint32_t)w1_slab, w1full_bar);
         }
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
             if (ptx::elect_one()) {
               const uint32_t slab16 = kSlabBytes >> 4;
 #pragma unroll
-              for (int t = 0; t < 3; ++t) {  // hi*hi, hi*lo, lo*hi
+              for (int t = 0; t < 3; ++t) {  // hi*hi, hi*lo, lo*hi (plain bf16: hi*hi only)
+                if (t > 0 && p.np == 1) break;
                 const uint32_t xa = s_lo + (t == 2 ? slab16 : 0u);
                 const uint32_t wb = s_lo + 2u * slab16 + (t == 1 ? slab16 : 0u);
 #pragma unroll
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
             const uint32_t hslab16 = kSlabBytes >> 4, wslab16 = (uint32_t)(p.n1 * kRowBytes) >> 4;
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
+              if (t > 0 && p.np == 1) break;
               const uint32_t hp = t == 2 ? 1u : 0u, wp = t == 1 ? 1u : 0u;
 #pragma unroll
               for (int j = 0; j < 2; ++j)
@@ -277,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
             const int chunk8 = half * 4 + cj;  // logical 16-byte chunk within the 128-byte row
             const int off = (chunk8 ^ (row & 7)) << 4;
             *reinterpret_cast<uint4*>(hrow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(hrow + 2 * kSlabBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (p.np == 2)
+              *reinterpret_cast<uint4*>(hrow + 2 * kSlabBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         ptx::tc_fence_before();
@@ -347,7 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) ae_umma_kernel(const AeParams p) 
 
 // fp32 rows -> hi/lo bf16 planes in slab format: [tile][plane][kb] x 16 KB; rows past `n` are zero.
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ rows, int64_t n, int64_t n_pad,
-                                                         int dim, int nkb, unsigned char* __restrict__ slabs) {
+                                                         int dim, int nkb, int np,
+                                                         unsigned char* __restrict__ slabs) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_pad) return;
@@ -366,7 +373,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
     }
     const int64_t off = (int64_t)(kc >> 3) * kSlabBytes + slab_chunk_offset(rin, kc & 7);
     *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(tile + (int64_t)nkb * kSlabBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (np == 2)
+      *reinterpret_cast<uint4*>(tile + (int64_t)nkb * kSlabBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -420,18 +428,19 @@ void ae_umma_weight_slabs(const float* w, int rows_out, int k_in, int slab_rows,
   }
 }
 
-int launch_ae_split_rows(const float* x, int64_t m, int d_in, unsigned char* slabs, cudaStream_t st) {
+int launch_ae_split_rows(const float* x, int64_t m, int d_in, int n_planes, unsigned char* slabs, cudaStream_t st) {
   const int64_t m_pad = round_up64(m, kBlockRows);
   const unsigned grid = (unsigned)((m_pad + 7) / 8);
-  split_rows_kernel<<<grid, 256, 0, st>>>(x, m, m_pad, d_in, d_in / 64, slabs);
+  split_rows_kernel<<<grid, 256, 0, st>>>(x, m, m_pad, d_in, d_in / 64, n_planes, slabs);
   LK_CHECK_LAUNCH("split_rows_kernel");
   return LK_OK;
 }
 
 int launch_ae_umma(const unsigned char* x_slabs, int64_t m, int d_in, int d_hidden, int d_latent,
                    const unsigned char* w0_slabs, const unsigned char* w1_slabs, const float* b0, const float* b1,
-                   int l2norm, float* z, int* err_flag, int sm_count, cudaStream_t st) {
+                   int l2norm, int n_planes, float* z, int* err_flag, int sm_count, cudaStream_t st) {
   AeParams p;
+  p.np = n_planes == 1 ? 1 : 2;
   p.x_slabs = x_slabs;
   p.w0_slabs = w0_slabs;
   p.w1_slabs = w1_slabs;

@@ -134,6 +134,7 @@ struct lk_ae {
   int device = 0, sm_count = 0;
   int kind = 0, d_in = 0, d_hidden = 0, d_latent = 0;
   int kernel = LK_KERNEL_AUTO;  // AUTO/UMMA: split-bf16 tensor-core kernel when the dims allow; SIMT: fp32 FMA
+  int precision = LK_F32;       // tensor-core kernel: LK_F32 = split-bf16 operands (3 MMAs), LK_BF16 = plain bf16
   float *w0t = nullptr, *b0 = nullptr, *w1t = nullptr, *b1 = nullptr;
   unsigned char *w0_slabs = nullptr, *w1_slabs = nullptr;
   int* err_flag = nullptr;
@@ -693,6 +694,16 @@ int lk_ae_set_kernel(lk_ae* ae, int kernel) {
   return LK_OK;
 }
 
+int lk_ae_set_precision(lk_ae* ae, int precision) {
+  if (!ae || (precision != LK_F32 && precision != LK_BF16)) return LK_ERR_INVALID;
+  if (precision == LK_BF16 && !ae->w0_slabs) {
+    set_error("lk_ae_set_precision: bf16 operands need the tensor-core encoder (d_in %% 64 == 0, d_hidden %% 128 == 0, d_latent <= 64)");
+    return LK_ERR_UNSUPPORTED;
+  }
+  ae->precision = precision;
+  return LK_OK;
+}
+
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream) {
   if (!ae || m < 0 || (m > 0 && (!x || !z)) || (x_mem != LK_HOST && x_mem != LK_DEVICE) ||
       (z_mem != LK_HOST && z_mem != LK_DEVICE)) {
@@ -710,7 +721,8 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
   int which = ae->kernel;
   if (env && !strcmp(env, "simt")) which = LK_KERNEL_SIMT;
   if (env && !strcmp(env, "umma")) which = LK_KERNEL_UMMA;
-  const bool use_umma = ae->w0_slabs && (which == LK_KERNEL_UMMA || (which == LK_KERNEL_AUTO && m >= 2 * kBlockRows));
+  const bool use_umma = ae->w0_slabs && (which == LK_KERNEL_UMMA || ae->precision == LK_BF16 ||
+                                         (which == LK_KERNEL_AUTO && m >= 2 * kBlockRows));
   for (int64_t done = 0; done < m; done += step) {
     const int64_t cnt = m - done < step ? m - done : step;
     const float* xin = x + (size_t)done * ae->d_in;
@@ -727,9 +739,10 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
     }
     if (use_umma) {
       if ((rc = ae->xslabs.ensure(ae_umma_x_slab_bytes(step, ae->d_in))) != LK_OK) return rc;
-      if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;
+      const int planes = ae->precision == LK_BF16 ? 1 : 2;
+      if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, planes, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;
       rc = launch_ae_umma(ae->xslabs.as<unsigned char>(), cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs,
-                          ae->w1_slabs, ae->b0, ae->b1, l2, zdev, ae->err_flag, ae->sm_count, st);
+                          ae->w1_slabs, ae->b0, ae->b1, l2, planes, zdev, ae->err_flag, ae->sm_count, st);
     } else {
       rc = launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1,
                             l2, zdev, st);

@@ -132,9 +132,10 @@ int launch_ae_encode(const float* x, int64_t m, int d_in, int d_hidden, int d_la
 // tensor-core (split-bf16) autoencoder path, lk_ae_umma.cu
 int ae_umma_supported(int d_in, int d_hidden, int d_latent);
 size_t ae_umma_x_slab_bytes(int64_t m, int d_in);
-int launch_ae_split_rows(const float* x, int64_t m, int d_in, unsigned char* slabs, cudaStream_t st);
+// n_planes: 2 = split-bf16 operands (x = hi + lo), 1 = plain bf16 (hi only)
+int launch_ae_split_rows(const float* x, int64_t m, int d_in, int n_planes, unsigned char* slabs, cudaStream_t st);
 int launch_ae_umma(const unsigned char* x_slabs, int64_t m, int d_in, int d_hidden, int d_latent,
                    const unsigned char* w0_slabs, const unsigned char* w1_slabs, const float* b0, const float* b1,
-                   int l2norm, float* z, int* err_flag, int sm_count, cudaStream_t st);
+                   int l2norm, int n_planes, float* z, int* err_flag, int sm_count, cudaStream_t st);
 
 }  // namespace lk

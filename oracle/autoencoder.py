@@ -38,11 +38,14 @@ def load_encoder_weights(state_dict: Mapping[str, object], kind: str) -> Dict[st
     return out
 
 
-def ae_encode(x: torch.Tensor, w: Mapping[str, torch.Tensor], kind: str) -> torch.Tensor:
-    """Latent code used for retrieval: fp32 [M, Z].  For the VAE this is `mu`."""
+def ae_encode(x: torch.Tensor, w: Mapping[str, torch.Tensor], kind: str, precision: str = "fp32") -> torch.Tensor:
+    """Latent code used for retrieval: fp32 [M, Z].  For the VAE this is `mu`.
+    precision="bf16": the reference's arithmetic fed bf16-rounded inputs, weights and hidden
+    activations (what the engine's opt-in bf16 encoder computes; fp32 accumulation, fp32 biases)."""
     x = x.detach().to("cpu", torch.float32)
-    h = torch.relu(F.linear(x, w["w0"], w["b0"]))
-    z = F.linear(h, w["w1"], w["b1"])
+    r = (lambda t: t.to(torch.bfloat16).to(torch.float32)) if precision == "bf16" else (lambda t: t)
+    h = torch.relu(F.linear(r(x), r(w["w0"]), w["b0"]))
+    z = F.linear(r(h), r(w["w1"]), w["b1"])
     if kind == "cae":
         z = F.normalize(z, p=2, dim=-1)
     return z

@@ -360,6 +360,30 @@ def test_ae_tensor_core_encoder_matches_oracle(lrb, kind, m):
         assert torch.allclose(z.norm(dim=-1), torch.ones(m), atol=1e-6)
 
 
+@pytest.mark.parametrize("kind", ["vae", "dae", "cae"])
+def test_ae_bf16_precision_matches_the_reference_fed_bf16_values(lrb, kind):
+    """The opt-in bf16 encoder (one MMA per product) against the reference's arithmetic fed
+    bf16-rounded inputs, weights and hidden activations: fp32 accumulation on both sides, so
+    they agree to 2e-5 of the row scale apart from hidden activations that round the other way
+    (a different summation order can move a value across a bf16 rounding boundary: 2^-9 of one
+    of 512 terms)."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    ae = lrb.load_autoencoder(kind, os.path.join(gold, f"ae_weights_{kind}.npz")).set_precision("bf16")
+    rng = np.random.default_rng(55)
+    x = torch.from_numpy(rng.standard_normal((3000, 384)).astype(np.float32))
+    x /= x.norm(dim=1, keepdim=True)
+    take = lambda z: z[0] if isinstance(z, tuple) else z
+    z = take(ae.encode(x.cuda())).cpu()
+    w = oracle.load_encoder_weights(np.load(os.path.join(gold, f"ae_weights_{kind}.npz")), kind)
+    ref = oracle.ae_encode(x, w, kind, precision="bf16")
+    err = (z - ref).abs() / ref.abs().amax(dim=1, keepdim=True)
+    assert err.max().item() < 2e-3 and (err > 2e-5).float().mean().item() < 0.02, (err.max().item(), (err > 2e-5).float().mean().item())
+    ref32 = oracle.ae_encode(x, w, kind)
+    assert ((z - ref32).abs() / ref32.abs().amax(dim=1, keepdim=True)).max().item() < 2e-2  # bf16-level vs fp32
+    z32 = take(ae.set_precision("fp32").encode(x.cuda())).cpu()
+    assert ((z32 - ref32).abs() / ref32.abs().amax(dim=1, keepdim=True)).max().item() < 3e-5
+
+
 def test_ae_tensor_core_kernel_is_rejected_for_unsupported_dims(lrb):
     rng = np.random.default_rng(4)
     sd = {"encoder.0.weight": rng.standard_normal((8, 16)).astype(np.float32),

@@ -3,10 +3,10 @@ import argparse, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import latent_rag_b200 as lrb
-ap = argparse.ArgumentParser(); ap.add_argument("--rows", type=int, default=1_000_000); ap.add_argument("--kernel", default="umma"); ap.add_argument("--iters", type=int, default=5)
+ap = argparse.ArgumentParser(); ap.add_argument("--rows", type=int, default=1_000_000); ap.add_argument("--kernel", default="umma"); ap.add_argument("--iters", type=int, default=5); ap.add_argument("--precision", default="fp32")
 a = ap.parse_args()
 gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
-ae = lrb.load_autoencoder("cae", os.path.join(gold, "ae_weights_cae.npz"), device=0).set_kernel(a.kernel)
+ae = lrb.load_autoencoder("cae", os.path.join(gold, "ae_weights_cae.npz"), device=0).set_kernel(a.kernel).set_precision(a.precision)
 x = torch.randn((a.rows, 384), device="cuda"); x /= x.norm(dim=1, keepdim=True)
 ae.encode(x[:4096]); torch.cuda.synchronize()
 for it in range(a.iters):
