@@ -441,6 +441,8 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if ((rc = ix->q_side.ensure((size_t)b_pad * sizeof(float))) != LK_OK) return rc;
   // no clearing: padded query rows only feed accumulator lanes nobody reads, and the K padding of
   // the real rows is written by the tiling kernel
+  if (const char* e = getenv("LK_DBG"))
+    if (atoi(e) & 8) LK_CUDA(cudaMemsetAsync(ix->q_tiles.p, 0x7F, qt_bytes, st));  // test aid: huge garbage
   rc = ingest_rows(ix, queries, q_dtype, q_mem, b, ix->q_tiles.p, ix->q_side.as<float>(), 0, st);
   if (rc != LK_OK) return rc;
 
@@ -510,6 +512,12 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (which != LK_KERNEL_UMMA) {
     LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
     LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
+  } else if (const char* e = getenv("LK_DBG")) {
+    if (atoi(e) & 8) {  // test aid: poison what the kernel must not rely on (huge scores, valid-looking ids / counts)
+      LK_CUDA(cudaMemsetAsync(a.part_scores, 0x7F, n_part * sizeof(float), st));
+      LK_CUDA(cudaMemsetAsync(a.part_idx, 0x00, n_part * sizeof(int32_t), st));
+      if (a.part_cnt) LK_CUDA(cudaMemsetAsync(a.part_cnt, 0x01, n_cnt * sizeof(int), st));
+    }
   }
   if (which == LK_KERNEL_UMMA) rc = launch_search_umma(a, ix->sm_count, st);
   else rc = launch_search_simt(a, ix->sm_count, st);

@@ -156,6 +156,23 @@ def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
     _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
 
 
+@pytest.mark.parametrize("n,b,dim,k", [(20000, 700, 384, 10), (20000, 700, 64, 50), (5000, 130, 768, 10), (300, 1, 64, 128)])
+def test_scratch_buffers_are_not_relied_on(lrb, n, b, dim, k, monkeypatch):
+    """The tcgen05 path clears neither the padded query rows nor the partial lists before a launch
+    (query tiles that span fewer scheduling groups than others leave list slots the kernel itself
+    has to mark empty).  LK_DBG=8 poisons all of it with huge scores, valid-looking ids and counts."""
+    monkeypatch.setenv("LK_FORCE_KERNEL", "umma")
+    monkeypatch.setenv("LK_DBG", "8")
+    rng = np.random.default_rng(n + b)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric="euclidean")
+    for _ in range(2):  # the second call reuses the (now dirty) workspaces
+        d, i = r.search(q, k)
+        d_ref, i_ref = _oracle(emb, q, k, "euclidean")
+        _assert_topk(d_ref, i_ref, d, i, l2=(emb, q))
+
+
 @pytest.mark.parametrize("n,b,dim,k", [(1000, 50, 32, 5), (20000, 33, 384, 10), (3000, 9, 768, 100), (700, 5, 48, 128)])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 @pytest.mark.parametrize("metric", ["cosine", "euclidean"])
