@@ -124,6 +124,9 @@ struct lk_index {
   float* side = nullptr;
   double* whiten = nullptr;
   int* err_flag = nullptr;
+  int* ticket = nullptr;  // completion counters of the single-launch small-batch search
+  unsigned char* pin = nullptr;  // pinned, device-visible host staging of that path: queries | scores | ids
+  size_t pin_cap = 0;
   Buf stage, white, q_tiles, q_side, part_s, part_i, part_c, out_s, out_i, debug;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -167,6 +170,8 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->side) cudaFree(ix->side);
   if (ix->whiten) cudaFree(ix->whiten);
   if (ix->err_flag) cudaFree(ix->err_flag);
+  if (ix->ticket) cudaFree(ix->ticket);
+  if (ix->pin) cudaFreeHost(ix->pin);
   Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->part_c,
                  &ix->out_s, &ix->out_i, &ix->debug};
   for (Buf* b : bufs) b->release();
@@ -230,6 +235,8 @@ int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, 
   LK_CREATE_CUDA(cudaMemset(ix->tiles, 0, tile_bytes));
   LK_CREATE_CUDA(cudaMemset(ix->side, 0xFF, side_bytes));  // NaN: rows that do not exist never rank
   LK_CREATE_CUDA(cudaMemset(ix->err_flag, 0, sizeof(int)));
+  LK_CREATE_CUDA(cudaMalloc((void**)&ix->ticket, 16 * sizeof(int)));
+  LK_CREATE_CUDA(cudaMemset(ix->ticket, 0, 16 * sizeof(int)));
   if (whiten) {
     const size_t wb = (size_t)dim * dim * sizeof(double);
     LK_CREATE_CUDA(cudaMalloc((void**)&ix->whiten, wb));
@@ -434,6 +441,82 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
 
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[0], st));
 
+  // 0. A few queries over a small corpus (the reference's own caller issues ONE query per call,
+  // main.py:270-271): everything in one launch -- query rounding and norms, search, merge of the
+  // slices -- instead of tiling kernel + search + merge kernel.
+  {
+    const char* fe = getenv("LK_FUSED");
+    const bool allow = kernel == LK_KERNEL_AUTO && !getenv("LK_FORCE_KERNEL") && !(fe && !atoi(fe));
+    if (allow && !ix->whiten && ix->storage == LK_BF16 && simt_fused_supported(ix->g, ix->n_rows, b, k)) {
+      SearchArgs a = {};
+      a.tiles = ix->tiles;
+      a.side = ix->side;
+      a.n_rows = ix->n_rows;
+      a.g = ix->g;
+      a.n_queries = b;
+      a.metric = ix->kmetric;
+      a.k = k;
+      a.idx_base = idx_base;
+      a.ticket = ix->ticket;
+      a.q_raw_dtype = q_dtype;
+      // Host buffers go through a pinned staging block; the results are written into it by the
+      // kernel itself (zero copy): one copy, a launch and one synchronisation instead of three copies.
+      const size_t q_bytes = ((size_t)b * ix->dim * (q_dtype == LK_F32 ? 4 : 2) + 15) / 16 * 16;
+      const size_t s_bytes = ((size_t)b * k * sizeof(float) + 15) / 16 * 16;
+      const size_t i_bytes = (size_t)b * k * sizeof(int64_t);
+      if (q_mem == LK_HOST || out_mem == LK_HOST) {
+        const size_t need = q_bytes + s_bytes + i_bytes;
+        if (need > ix->pin_cap) {
+          if (ix->pin) cudaFreeHost(ix->pin);
+          ix->pin = nullptr;
+          ix->pin_cap = 0;
+          LK_CUDA(cudaHostAlloc((void**)&ix->pin, need + 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+          ix->pin_cap = need + 4096;
+        }
+      }
+      if (q_mem == LK_HOST) {  // every slice reads the queries: they go to device memory, through the pinned block
+        const size_t qb = (size_t)b * ix->dim * (q_dtype == LK_F32 ? 4 : 2);
+        if ((rc = ix->stage.ensure(qb)) != LK_OK) return rc;
+        memcpy(ix->pin, queries, qb);
+        LK_CUDA(cudaMemcpyAsync(ix->stage.p, ix->pin, qb, cudaMemcpyHostToDevice, st));
+        a.q_raw = ix->stage.p;
+      } else {
+        a.q_raw = queries;
+      }
+      if ((rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel)) != LK_OK) return rc;
+      const size_t n_part = (size_t)b * a.n_lists * a.ksel;  // every slice writes its whole lists: no clearing
+      if ((rc = ix->part_s.ensure(n_part * sizeof(float))) != LK_OK) return rc;
+      if ((rc = ix->part_i.ensure(n_part * sizeof(int32_t))) != LK_OK) return rc;
+      a.part_scores = ix->part_s.as<float>();
+      a.part_idx = ix->part_i.as<int32_t>();
+      a.out_scores = out_scores;
+      a.out_idx = out_idx;
+      if (out_mem == LK_HOST) {
+        a.out_scores = reinterpret_cast<float*>(ix->pin + q_bytes);
+        a.out_idx = reinterpret_cast<int64_t*>(ix->pin + q_bytes + s_bytes);
+      }
+      if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
+      if ((rc = launch_search_simt(a, ix->sm_count, st)) != LK_OK) return rc;
+      if (ix->timing) {
+        LK_CUDA(cudaEventRecord(ix->ev[2], st));
+        LK_CUDA(cudaEventRecord(ix->ev[3], st));
+      }
+      if (out_mem == LK_HOST) {
+        LK_CUDA(cudaStreamSynchronize(st));
+        memcpy(out_scores, a.out_scores, (size_t)b * k * sizeof(float));
+        memcpy(out_idx, a.out_idx, (size_t)b * k * sizeof(int64_t));
+      } else if (q_mem == LK_HOST) {
+        LK_CUDA(cudaStreamSynchronize(st));  // the staged queries must outlive the kernel
+      }
+      if (ix->timing) {
+        LK_CUDA(cudaEventSynchronize(ix->ev[3]));
+        LK_CUDA(cudaEventElapsedTime(&ix->last_search_ms, ix->ev[1], ix->ev[2]));
+        LK_CUDA(cudaEventElapsedTime(&ix->last_total_ms, ix->ev[0], ix->ev[3]));
+      }
+      return LK_OK;
+    }
+  }
+
   // 1. queries -> tiles (+ side values), same geometry and rounding as the corpus
   const int64_t b_pad = round_up64(b, 2 * kBlockRows);  // whole PAIRS of query tiles (CTA-pair kernel)
   const size_t qt_bytes = (size_t)(b_pad / kBlockRows) * ix->g.block_bytes();
@@ -447,7 +530,7 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (rc != LK_OK) return rc;
 
   // 2. plan + partial lists
-  SearchArgs a;
+  SearchArgs a = {};
   a.tiles = ix->tiles;
   a.side = ix->side;
   a.n_rows = ix->n_rows;

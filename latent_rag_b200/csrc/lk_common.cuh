@@ -108,10 +108,20 @@ struct SearchArgs {
   int* err_flag;           // device int, set non-zero by a kernel that timed out
   const float* seed;       // tcgen05 kernel, k > 32: [n_queries, k] scores of a sample search, or null
   float* debug_tile;       // optional [128 x 128] dump of unit 0's raw accumulator (bring-up aid)
+  // single-launch mode of the SIMT kernel (small batches on small corpora): raw queries in, final
+  // results out -- query rounding / norms, search and the merge of the slices in one kernel
+  const void* q_raw;       // [n_queries, dim] row-major device memory (q_tiles unused), or null
+  int q_raw_dtype;         // LK_F32 / LK_BF16
+  float* out_scores;       // [n_queries, k]
+  int64_t* out_idx;        // [n_queries, k]   row position + idx_base
+  int64_t idx_base;
+  int* ticket;             // one zero-initialised counter per query group; the last slice to finish merges
 };
 
 int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
 int launch_search_simt(const SearchArgs& a, int sm_count, cudaStream_t st);
+// whether the single-launch mode serves this call (bf16 storage, <= 4 queries, a corpus of at most 256 MB)
+int simt_fused_supported(const TileGeom& g, int64_t n_rows, int64_t n_queries, int k);
 int umma_supported(const TileGeom& g, int k);
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
 // rows of the corpus prefix whose top-k seeds the selection thresholds (0 = do not seed)

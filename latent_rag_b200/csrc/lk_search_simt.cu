@@ -42,15 +42,16 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 
 // grid = (n_slices, ceil(B / QG)); 128 threads; thread t owns row t of each row block of
 // the slice, warp g owns the top-k list of query g of the group.
-template <typename ElemT, int QG>
+template <typename ElemT, int QG, bool FUSED>
 __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, int blocks_per_slice) {
   constexpr int E = Chunk<ElemT>::E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int dim_pad = a.g.dim_pad;
   float* qs = reinterpret_cast<float*>(smem_raw);                 // [QG][dim_pad]
   float* sc = qs + QG * dim_pad;                                  // [QG][128]
-  float* ls = sc + QG * kBlockRows;                               // [QG][k]
-  int32_t* li = reinterpret_cast<int32_t*>(ls + QG * a.k);        // [QG][k]
+  constexpr int kLists = FUSED && QG == 1 ? kBlockRows / 32 : QG;  // single-launch merge: one list per warp
+  float* ls = sc + QG * kBlockRows;                               // [kLists][k]
+  int32_t* li = reinterpret_cast<int32_t*>(ls + kLists * a.k);    // [kLists][k]
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int slice = blockIdx.x;
@@ -60,9 +61,38 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
   const int64_t blk_hi = min(nblk, blk_lo + blocks_per_slice);
   const int64_t block_bytes = a.g.block_bytes();
 
+  float qside[QG];
+  if (FUSED) {
+    // raw queries: round to the storage type like the tiling kernel does, and compute the side
+    // value with ITS order of operations (one warp per query: lane-strided fmaf chain, xor-shuffle
+    // sum), so the scores equal those of the tiled path bit for bit
+    for (int i = t; i < QG * dim_pad; i += kBlockRows) {
+      const int g = i / dim_pad, c = i - g * dim_pad;
+      const int64_t q = q0 + g;
+      float v = 0.f;
+      if (q < a.n_queries && c < a.g.dim) {
+        v = a.q_raw_dtype == LK_F32 ? static_cast<const float*>(a.q_raw)[q * a.g.dim + c]
+                                    : __bfloat162float(static_cast<const __nv_bfloat16*>(a.q_raw)[q * a.g.dim + c]);
+        if (sizeof(ElemT) == 2) v = __bfloat162float(__float2bfloat16_rn(v));
+      }
+      qs[i] = v;
+    }
+    __syncthreads();
+    if (warp < QG) {
+      float ss = 0.f;
+      for (int c = lane; c < a.g.dim; c += 32) ss = fmaf(qs[warp * dim_pad + c], qs[warp * dim_pad + c], ss);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) sc[warp] = a.metric == LK_COSINE ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : ss;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < QG; ++g) qside[g] = sc[g];
+    __syncthreads();
+  }
   // stage the group's queries as fp32 (gather out of the query tiles)
   const unsigned char* qt = static_cast<const unsigned char*>(a.q_tiles);
-  for (int i = t; i < QG * dim_pad; i += kBlockRows) {
+  for (int i = t; !FUSED && i < QG * dim_pad; i += kBlockRows) {
     const int g = i / dim_pad, c = i - g * dim_pad;
     const int64_t q = q0 + g;
     float v = 0.f;
@@ -75,9 +105,10 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
     }
     qs[i] = v;
   }
-  float qside[QG];
+  if (!FUSED) {
 #pragma unroll
-  for (int g = 0; g < QG; ++g) qside[g] = (q0 + g < a.n_queries) ? a.q_side[q0 + g] : 0.f;
+    for (int g = 0; g < QG; ++g) qside[g] = (q0 + g < a.n_queries) ? a.q_side[q0 + g] : 0.f;
+  }
   if (warp < QG) warp_list_init<int32_t>(ls + warp * a.k, li + warp * a.k, a.k, lane);
   __syncthreads();
 
@@ -117,7 +148,27 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
       sc[g * kBlockRows + t] = s;
     }
     __syncthreads();
-    if (warp < QG && q0 + warp < a.n_queries) {
+    if (FUSED && blocks_per_slice == 1) {
+      // one row block per slice (small corpora): no running list to maintain -- every thread ranks
+      // its own score among the 128 (all-pairs, shared-memory broadcasts) and the best k land in
+      // the list sorted; ~1 us instead of tens of serial list insertions
+#pragma unroll
+      for (int g = 0; g < QG; ++g) {
+        const float v = sc[g * kBlockRows + t];
+        int rank = kBlockRows;  // NaN (a row past the end): never selected
+        if (v == v) {
+          rank = 0;
+          for (int u = 0; u < kBlockRows; ++u) {
+            const float su = sc[g * kBlockRows + u];
+            rank += (su > v || (su == v && u < t)) ? 1 : 0;
+          }
+        }
+        if (rank < a.k) {
+          ls[g * a.k + rank] = v;
+          li[g * a.k + rank] = (int32_t)(blk * kBlockRows + t);
+        }
+      }
+    } else if (warp < QG && q0 + warp < a.n_queries) {
       float* s = ls + warp * a.k;
       int32_t* ix = li + warp * a.k;
 #pragma unroll
@@ -137,6 +188,146 @@ __global__ void __launch_bounds__(kBlockRows) simt_search_kernel(SearchArgs a, i
       a.part_idx[o + j] = li[warp * a.k + j];
     }
   }
+  if (!FUSED) return;
+  // The slice that finishes last merges all slices' lists of its query group and writes the final
+  // result (threadFenceReduction pattern: lists, fence, ticket).
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const int n_slices = (int)gridDim.x;
+    const int done = atomicAdd(a.ticket + blockIdx.y, 1);
+    s_last = done == n_slices - 1;
+    if (s_last) a.ticket[blockIdx.y] = 0;  // ready for the next call
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // Final merge by the last slice.  Every list is sorted best first, so T = the largest k-th entry
+  // over the slices bounds the global k-th best from below (that slice alone holds k rows >= T):
+  // only candidates >= T can be in the result.  They are gathered (a few dozen, typically) and
+  // ranked all-pairs under (score desc, index asc).  If more than kGather qualify (heavy ties),
+  // the warps fall back to folding all candidates through sorted lists.
+  constexpr int kGather = 512;
+  float* gs = reinterpret_cast<float*>(li + kLists * a.k);   // [kGather] gathered scores
+  int32_t* gi = reinterpret_cast<int32_t*>(gs + kGather);    // [kGather] gathered ids
+  __shared__ float s_thr;
+  __shared__ int s_thr_key;  // order-preserving key of the best bound, >> 1 so that it fits a signed atomicMax
+  __shared__ int s_n;
+  constexpr int kMaxSlices = 512;
+  float* gi_end = reinterpret_cast<float*>(gi + kGather);
+  const int n_slices = (int)gridDim.x;
+  if (t == 0) s_thr_key = 0;
+  __syncthreads();
+  for (int g = 0; g < QG; ++g) {
+    const int64_t q = q0 + g;
+    if (q >= a.n_queries) break;  // block-uniform
+    const float* ps = a.part_scores + q * a.n_lists * a.ksel;
+    const int32_t* pi = a.part_idx + q * a.n_lists * a.ksel;
+    // Lower bounds of the global k-th best: for a depth j, the ceil(k / j)-th largest of the
+    // slices' j-th entries (that many slices hold j rows each at or above it).  Depths 1, 2, 4, 8
+    // and k are tried -- one batch of loads -- and the largest bound wins; with 128-row slices the
+    // k-th entries alone (depth k) would let through hundreds of candidates.
+    constexpr int kDepths = 5;
+    float* col = gi_end;  // [kDepths][kMaxSlices] staged entries
+    const int depth[kDepths] = {1, 2, 4, 8, a.k};
+    if (t == 0) {
+      s_n = 0;
+      s_thr = -INFINITY;
+    }
+    for (int sl = t; sl < n_slices; sl += kBlockRows)
+#pragma unroll
+      for (int d = 0; d < kDepths; ++d)
+        col[d * kMaxSlices + sl] = depth[d] <= a.k ? __ldcg(ps + (int64_t)sl * a.ksel + (depth[d] - 1)) : -INFINITY;
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < kDepths; ++d) {
+      const int need = (a.k + depth[d] - 1) / depth[d];  // slices that must reach the bound
+      if (depth[d] > a.k || need > n_slices) continue;
+      for (int sl = t; sl < n_slices; sl += kBlockRows) {
+        const float v = col[d * kMaxSlices + sl];
+        int rank = 0;
+        for (int u = 0; u < n_slices; ++u) {
+          const float w = col[d * kMaxSlices + u];
+          rank += (w > v || (w == v && u < sl)) ? 1 : 0;
+        }
+        if (rank == need - 1) atomicMax(reinterpret_cast<int*>(&s_thr_key), (int)(order_key(v) >> 1));
+      }
+    }
+    __syncthreads();
+    float thr = s_thr_key > 0 ? order_key_inv(((uint32_t)s_thr_key << 1)) : -INFINITY;  // rounded DOWN: still a lower bound
+    __syncthreads();
+    if (t == 0) s_thr_key = 0;
+    const int n_cand = n_slices * a.k;
+    for (int c0 = t; c0 < n_cand; c0 += kBlockRows * 8) {  // eight independent loads in flight per thread
+      float v[8];
+      int64_t off[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * kBlockRows;
+        v[u] = -INFINITY;
+        off[u] = 0;
+        if (c < n_cand) {
+          const int sl = c / a.k, e = c - sl * a.k;
+          off[u] = (int64_t)sl * a.ksel + e;
+          v[u] = __ldcg(ps + off[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (c0 + u * kBlockRows < n_cand && v[u] >= thr) {
+          const int32_t id = __ldcg(pi + off[u]);
+          if (id >= 0 && id != IdxTraits<int32_t>::sentinel()) {
+            const int pos = atomicAdd(&s_n, 1);
+            if (pos < kGather) {
+              gs[pos] = v[u];
+              gi[pos] = id;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n <= kGather) {
+      for (int j = t; j < a.k; j += kBlockRows) {  // fewer than k candidates exist: padding
+        a.out_scores[q * a.k + j] = -INFINITY;
+        a.out_idx[q * a.k + j] = -1;
+      }
+      __syncthreads();
+      for (int i = t; i < n; i += kBlockRows) {
+        const float v = gs[i];
+        const int32_t id = gi[i];
+        int rank = 0;
+        for (int u = 0; u < n; ++u) rank += (gs[u] > v || (gs[u] == v && gi[u] < id)) ? 1 : 0;
+        if (rank < a.k) {
+          a.out_scores[q * a.k + rank] = v;
+          a.out_idx[q * a.k + rank] = (int64_t)id + a.idx_base;
+        }
+      }
+    } else if (warp == 0) {  // heavy ties at the threshold: one warp, sorted-list insertion
+      float* s = ls;
+      int32_t* ix = li;
+      warp_list_init<int32_t>(s, ix, a.k, lane);
+      for (int base = 0; base < n_cand; base += 32) {
+        const int c = base + lane;
+        float v = 0.f;
+        int32_t id = -1;
+        if (c < n_cand) {
+          const int sl = c / a.k, e = c - sl * a.k;
+          v = __ldcg(ps + (int64_t)sl * a.ksel + e);
+          id = __ldcg(pi + (int64_t)sl * a.ksel + e);
+        }
+        warp_list_offer<int32_t>(s, ix, a.k, v, id, c < n_cand && id >= 0 && id != IdxTraits<int32_t>::sentinel(), lane);
+      }
+      for (int j = lane; j < a.k; j += 32) {
+        const bool filled = ix[j] != IdxTraits<int32_t>::sentinel();
+        a.out_scores[q * a.k + j] = s[j];
+        a.out_idx[q * a.k + j] = filled ? (int64_t)ix[j] + a.idx_base : (int64_t)-1;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 int slices_for(const SearchArgs& a, int sm_count, int qg, int* blocks_per_slice) {
@@ -145,6 +336,7 @@ int slices_for(const SearchArgs& a, int sm_count, int qg, int* blocks_per_slice)
   int64_t want = ((int64_t)sm_count * 8 + groups - 1) / groups;  // ~8 CTAs per SM overall
   if (want < 1) want = 1;
   if (want > 1024) want = 1024;
+  if (a.q_raw != nullptr && want > 512) want = 512;  // the single-launch merge stages one value per slice
   if (want > nblk) want = nblk;
   if (want < 1) want = 1;
   const int64_t bps = (nblk + want - 1) / want;
@@ -157,6 +349,11 @@ int slices_for(const SearchArgs& a, int sm_count, int qg, int* blocks_per_slice)
 inline int simt_qg(const SearchArgs& a) { return a.n_queries >= 2 ? kSimtQG : 1; }
 
 }  // namespace
+
+int simt_fused_supported(const TileGeom& g, int64_t n_rows, int64_t n_queries, int k) {
+  return g.elem_bytes == 2 && n_queries >= 1 && n_queries <= kSimtQG && k >= 1 && k <= kMaxK &&
+         n_rows * (int64_t)g.dim_pad * 2 <= (256ll << 20);
+}
 
 int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {
   int bps;
@@ -179,18 +376,27 @@ int launch_search_simt(const SearchArgs& a, int sm_count, cudaStream_t st) {
     set_error("simt search: batch of %lld queries is too large for one launch", (long long)a.n_queries);
     return LK_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)qg * (a.g.dim_pad + kBlockRows + 2 * a.k) * 4;
+  const int n_lists_smem = a.q_raw != nullptr && qg == 1 ? kBlockRows / 32 : qg;
+  const size_t smem = ((size_t)qg * (a.g.dim_pad + kBlockRows) + (size_t)n_lists_smem * 2 * a.k) * 4 +
+                      (a.q_raw != nullptr ? 512 * 8 + 5 * 512 * 4 : 0);  // single-launch merge: gathered candidates, bounds
   const dim3 grid((unsigned)slices, (unsigned)groups);
-#define LK_SIMT(T, QG)                                                                              \
+#define LK_SIMT(T, QG, FU)                                                                          \
   do {                                                                                              \
-    LK_CUDA(cudaFuncSetAttribute(simt_search_kernel<T, QG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)smem));                                                       \
-    simt_search_kernel<T, QG><<<grid, kBlockRows, smem, st>>>(a, bps);                              \
+    if (smem > 48 * 1024)                                                                           \
+      LK_CUDA(cudaFuncSetAttribute(simt_search_kernel<T, QG, FU>,                                   \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    simt_search_kernel<T, QG, FU><<<grid, kBlockRows, smem, st>>>(a, bps);                          \
   } while (0)
-  if (a.g.elem_bytes == 2) {
-    if (qg == 1) LK_SIMT(__nv_bfloat16, 1); else LK_SIMT(__nv_bfloat16, kSimtQG);
+  if (a.q_raw != nullptr) {  // single-launch mode
+    if (a.g.elem_bytes != 2 || !a.ticket || !a.out_scores || !a.out_idx || groups != 1) {
+      set_error("simt search: the single-launch mode needs bf16 storage and one query group");
+      return LK_ERR_INVALID;
+    }
+    if (qg == 1) LK_SIMT(__nv_bfloat16, 1, true); else LK_SIMT(__nv_bfloat16, kSimtQG, true);
+  } else if (a.g.elem_bytes == 2) {
+    if (qg == 1) LK_SIMT(__nv_bfloat16, 1, false); else LK_SIMT(__nv_bfloat16, kSimtQG, false);
   } else {
-    if (qg == 1) LK_SIMT(float, 1); else LK_SIMT(float, kSimtQG);
+    if (qg == 1) LK_SIMT(float, 1, false); else LK_SIMT(float, kSimtQG, false);
   }
 #undef LK_SIMT
   LK_CHECK_LAUNCH("simt_search_kernel");

@@ -156,6 +156,37 @@ def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
     _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
 
 
+@pytest.mark.parametrize("n,b,dim,k", [(315, 1, 64, 10), (20000, 1, 384, 10), (20000, 4, 384, 30), (5003, 3, 100, 128),
+                                       (100, 2, 32, 5), (60000, 1, 768, 100)])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_single_launch_small_batch_path(lrb, n, b, dim, k, metric, monkeypatch):
+    """Up to 4 queries over a small corpus (how the reference's caller drives retrieve(), main.py:270-271)
+    take the single-launch path: raw queries in, final top-k out of one kernel.  Same results as
+    the oracle, as the general path (bit for bit against the SIMT kernel it shares its arithmetic
+    with), and as itself from host and device queries; repeated calls reuse the completion ticket."""
+    rng = np.random.default_rng(n * 3 + b)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(emb[rng.integers(0, n, b)] + 0.2 * torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric)
+    kk = min(k, n)
+    d_ref, i_ref = _oracle(emb, q, kk, metric)
+    launches0 = lrb._native.launch_count()
+    d, i = r.search(q, k)
+    assert lrb._native.launch_count() - launches0 == 1  # ONE kernel
+    _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
+    for _ in range(3):
+        d2, i2 = r.search(q.cuda(), k)
+        np.testing.assert_array_equal(i2, i)
+        np.testing.assert_array_equal(d2, d)
+    monkeypatch.setenv("LK_FUSED", "0")
+    ds, is_ = r.index.search(q, kk, kernel="simt")
+    np.testing.assert_array_equal(is_, i)
+    np.testing.assert_array_equal(ds, d)
+    if b == 1:
+        texts, scores, docids = r.retrieve(q[0], top_k=kk)
+        assert docids == i[0].tolist()
+
+
 @pytest.mark.parametrize("n,b,dim,k", [(20000, 700, 384, 10), (20000, 700, 64, 50), (5000, 130, 768, 10), (300, 1, 64, 128)])
 def test_scratch_buffers_are_not_relied_on(lrb, n, b, dim, k, monkeypatch):
     """The tcgen05 path clears neither the padded query rows nor the partial lists before a launch

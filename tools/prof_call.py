@@ -32,3 +32,10 @@ bench("ExactIndex.search(host tensor)", lambda: ix.search(q, k))
 bench("BruteForceRetriever.search(host tensor)", lambda: r.search(q, k))
 bench("BruteForceRetriever.retrieve(host 1-D tensor)", lambda: r.retrieve(q[0], top_k=k))
 ix.set_timing(True); ix.search(qd, k, device_out=True); print("device: kernel %.1f us, whole device side %.1f us" % tuple(1e3 * t for t in ix.last_timing()))
+for nn, dd in [(315, 64), (2000, 384)]:
+    e2 = torch.from_numpy(rng.standard_normal((nn, dd)).astype(np.float32))
+    r2 = lrb.BruteForceRetriever(e2, [""] * nn, None)
+    r2.index.set_timing(True); r2.index.search(e2[:1].cuda(), k, device_out=True); r2.index.search(e2[:1].cuda(), k, device_out=True)
+    print("N=%d D=%d device: kernel %.1f us, whole device side %.1f us" % ((nn, dd) + tuple(1e3 * t for t in r2.index.last_timing())))
+    r2.index.set_timing(False)
+    bench(f"N={nn} D={dd} BruteForceRetriever.retrieve", lambda: r2.retrieve(e2[0], top_k=k))
