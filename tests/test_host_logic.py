@@ -113,3 +113,48 @@ def test_shard_bounds():
         assert b == list(oracle.shard_bounds(n, w))
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_metric_input_encoding_and_names():
+    """Host half of the device metrics (latent_rag_b200/evaluation.py): ids of any hashable kind are
+    coded densely and consistently on both sides, ragged lists are padded with -1, the relevant
+    lists become a CSR; metric names parse like evaluation/retrieval_metrics.py:38-39."""
+    from latent_rag_b200.evaluation import _encode, _parse_metric
+
+    ret, off, rel = _encode([["a", "b", "a"], ["c"], []], [["b", "z"], [], ["a"]])
+    assert ret.shape == (3, 3) and ret.dtype == np.int64
+    assert ret[0].tolist() == [0, 1, 0] and ret[1].tolist() == [2, -1, -1] and ret[2].tolist() == [-1, -1, -1]
+    assert off.tolist() == [0, 2, 2, 3]
+    assert rel.tolist()[0] == 1 and rel.tolist()[2] == 0  # "b" and "a" keep their codes; "z" gets a new one
+    assert _parse_metric("Recall@10") == ("Recall", 10) and _parse_metric("mrr") == ("mrr", None)
+    with pytest.raises(ValueError, match="No metrics"):
+        lrb.evaluate_retrieval([[1]], [[1]], [])
+
+
+@pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a GPU")
+def test_new_entry_points_fail_loudly_without_a_device():
+    with pytest.raises(_native.NativeError):
+        lrb.evaluate_retrieval([[1, 2]], [[2]], ["mrr"])
+    with pytest.raises(_native.NativeError):
+        lrb.rank_positive(torch.randn(4, 8), torch.randn(4, 8))
+    with pytest.raises(_native.NativeError):
+        lrb.PeerExchange(0, 0, 1)
+
+
+def test_embedding_compressor_needs_a_base_encoder():
+    """The SBERT forward is out of scope: without sentence-transformers and without `model=` the
+    class says so instead of substituting something else."""
+    try:
+        import sentence_transformers  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="sentence-transformers"):
+            lrb.EmbeddingCompressor()
+
+
+def test_sharded_retriever_rejects_unknown_exchange():
+    import oracle
+
+    emb = torch.randn(20, 8)
+    fake = lambda q, k: oracle.bruteforce_search(oracle.bruteforce_build(emb), q, k)
+    with pytest.raises(ValueError, match="Unknown exchange"):
+        lrb.ShardedRetriever(emb, 0, "cosine", local_search=fake, merge=oracle.merge_topk, exchange="mpi")
