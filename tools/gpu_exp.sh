@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
-for R in 10000000 25000000 50000000 100000000; do
-echo "== rows=$R B=1"; python tools/prof_case.py --rows $R --dim 384 --batch 1 --iters 6 2>&1 | tail -3
+run() { echo "== $*"; python tools/prof_case.py "$@" --iters 4 2>&1 | tail -1; }
+for B in 1 64 4096; do
+run --rows 1250000 --dim 768 --batch $B --k 10 --metric euclidean
+run --rows 1250000 --dim 768 --batch $B --k 100 --metric euclidean
 done
+run --rows 1250000 --dim 768 --batch 1024 --k 100 --metric euclidean
+run --rows 1250000 --dim 768 --batch 1024 --k 10 --metric euclidean
