@@ -86,7 +86,6 @@ struct UmmaParams {
   uint32_t lbo, sbo;
   int dbg;
   int rotate;            // corpus rotation per query-tile group (rot_cut)
-  int keep_lists;        // evict-last stores for the append buffers (their total footprint is small)
 };
 
 __host__ __device__ inline int64_t unit_begin(int64_t c, int64_t total, int64_t grid) {
@@ -379,7 +378,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     // append buffers stay in L2 (evict-last) as long as all of them together leave most of it to
     // the corpus stream; at thousands of queries they would be 100 MB and push the row blocks the
     // scheduling groups share out of L2 (ncu, B=4096: hit rate 80 -> 49 %, HBM reads x3)
-    const uint64_t keep_policy = p.keep_lists ? ptx::policy_evict_last() : ptx::policy_evict_normal();
+    // (KSEL 1 is the same selector with plain stores: no policy operand in the append blocks; the
+    // compactions, which are rare, keep hinted stores with the normal policy)
+    const uint64_t keep_policy = KSEL == 0 ? ptx::policy_evict_last() : ptx::policy_evict_normal();
     float thr = INFINITY;
     float q_sd = 0.f;
     int* cnt_out = nullptr;
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
                 for (int j = 8 * g; j < 8 * g + 8; ++j) {  // pure predication: a vote + branch per column, or a
                   // uniform branch between hinted and plain stores, both measured ~25 % slower
                   const float sc = score(__uint_as_float(r[j]), sdc[j]);
-                  if (sc > thr) top.append(sc, row0 + chunk * 32 + j, keep_policy);  // thr fixed between compactions
+                  if (sc > thr) top.template append<KSEL == 0>(sc, row0 + chunk * 32 + j, keep_policy);  // thr fixed between compactions
                 }
               }
             }
@@ -694,8 +695,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.debug_tile = a.debug_tile;
   p.dbg = getenv("LK_DBG") ? atoi(getenv("LK_DBG")) : 0;
   p.rotate = (p.dbg & 4) ? 0 : 1;
-  p.keep_lists = (int64_t)a.n_queries * a.n_lists * a.ksel * 8 <= (48ll << 20) ? 1 : 0;
-  if (p.dbg & 16) p.keep_lists = 1;
+  const bool keep_lists = (p.dbg & 16) || (int64_t)a.n_queries * a.n_lists * a.ksel * 8 <= (48ll << 20);
   p.lbo = kLbo;
   p.sbo = kSbo;
   if (const char* e = getenv("LK_UMMA_LBO")) p.lbo = (uint32_t)atoi(e);  // bring-up overrides
@@ -742,8 +742,10 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   } while (0)
   if (ksel == 10) {
     if (qres) LK_UMMA_M(10, true); else LK_UMMA_M(10, false);
+  } else if (keep_lists) {
+    if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);  // KSEL 0 = BufSelector, lists kept in L2
   } else {
-    if (qres) LK_UMMA_M(0, true); else LK_UMMA_M(0, false);  // KSEL 0 = BufSelector
+    if (qres) LK_UMMA_M(1, true); else LK_UMMA_M(1, false);  // KSEL 1 = BufSelector, plain appends
   }
 #undef LK_UMMA_M
 #undef LK_UMMA_C

@@ -334,9 +334,15 @@ struct BufSelector {
   // precondition: v > thr (and note_max has seen v).  The stores carry an evict-last hint: a
   // list is touched every few microseconds while the corpus streams through L2, and a partially
   // written sector that gets evicted in between costs a DRAM fill plus a write-back per append.
+  template <bool HINT>
   __device__ __forceinline__ void append(float v, int32_t id, uint64_t keep_policy) {
-    ptx::st_hint(bs + cnt, v, keep_policy);
-    ptx::st_hint(bi + cnt, id, keep_policy);
+    if (HINT) {
+      ptx::st_hint(bs + cnt, v, keep_policy);
+      ptx::st_hint(bi + cnt, id, keep_policy);
+    } else {  // plain stores: the policy operand costs a register-to-uniform move per hinted store
+      bs[cnt] = v;
+      bi[cnt] = id;
+    }
     ++cnt;
   }
   // Whole warp: shrink the buffers of (at most `budget`) lanes holding more than `limit` entries.
@@ -357,6 +363,7 @@ struct BufSelector {
 };
 
 template <int KSEL> struct SelectorFor { using type = RegSelector<KSEL>; };
-template <> struct SelectorFor<0> { using type = BufSelector; };
+template <> struct SelectorFor<0> { using type = BufSelector; };  // appends with an L2 evict-last hint
+template <> struct SelectorFor<1> { using type = BufSelector; };  // plain appends (thousands of queries)
 
 }  // namespace lk
