@@ -120,7 +120,7 @@ struct SearchArgs {
 
 int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);
 int launch_search_simt(const SearchArgs& a, int sm_count, cudaStream_t st);
-// whether the single-launch mode serves this call (bf16 storage, <= 4 queries, a corpus of at most 256 MB)
+// whether the single-launch mode serves this call (bf16 storage, <= 4 queries, rows x queries <= 40k)
 int simt_fused_supported(const TileGeom& g, int64_t n_rows, int64_t n_queries, int k);
 int umma_supported(const TileGeom& g, int k);
 int umma_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel);

@@ -350,9 +350,12 @@ inline int simt_qg(const SearchArgs& a) { return a.n_queries >= 2 ? kSimtQG : 1;
 
 }  // namespace
 
+// Measured against the general path (query tiling + tcgen05 search + merge, ~90 us per call): the
+// single launch wins while rows x queries <= ~40k (B=1: 59 vs 87 us at 20k rows, 83 vs 99 at 35k;
+// B=4: 69 vs 89 us at 8k rows, 118 vs 98 at 20k), whatever the dimension.
 int simt_fused_supported(const TileGeom& g, int64_t n_rows, int64_t n_queries, int k) {
   return g.elem_bytes == 2 && n_queries >= 1 && n_queries <= kSimtQG && k >= 1 && k <= kMaxK &&
-         n_rows * (int64_t)g.dim_pad * 2 <= (256ll << 20);
+         n_rows * n_queries <= 40000 && n_rows * (int64_t)g.dim_pad * 2 <= (64ll << 20);
 }
 
 int simt_plan(const SearchArgs& a, int sm_count, int* n_lists, int* ksel) {

@@ -156,8 +156,8 @@ def test_umma_kernel_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
     _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
 
 
-@pytest.mark.parametrize("n,b,dim,k", [(315, 1, 64, 10), (20000, 1, 384, 10), (20000, 4, 384, 30), (5003, 3, 100, 128),
-                                       (100, 2, 32, 5), (60000, 1, 768, 100)])
+@pytest.mark.parametrize("n,b,dim,k", [(315, 1, 64, 10), (20000, 1, 384, 10), (9000, 4, 384, 30), (5003, 3, 100, 128),
+                                       (100, 2, 32, 5), (39000, 1, 768, 100)])
 @pytest.mark.parametrize("metric", ["cosine", "euclidean"])
 def test_single_launch_small_batch_path(lrb, n, b, dim, k, metric, monkeypatch):
     """Up to 4 queries over a small corpus (how the reference's caller drives retrieve(), main.py:270-271)
