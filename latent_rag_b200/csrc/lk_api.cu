@@ -552,17 +552,31 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
   if (rc != LK_OK) return rc;
-  // results land here (device): the caller's buffers, or staging for a host copy
+  const int merge_len = a.ksel > kMaxK ? a.ksel : (k < a.ksel ? k : a.ksel);
+  const int64_t seed_rows = which == LK_KERNEL_UMMA ? umma_seed_rows(a, ix->sm_count) : 0;
+  // results land here: the caller's device buffers; for host outputs a device staging buffer, or --
+  // small results that no later kernel reads back -- the pinned block, written by the merge kernel
+  // itself (zero copy: two device-to-host copies less per call)
   float* d_s = out_scores;
   int64_t* d_i = out_idx;
-  if (out_mem == LK_HOST) {
+  const size_t out_s_bytes = ((size_t)b * k * sizeof(float) + 15) / 16 * 16, out_i_bytes = (size_t)b * k * sizeof(int64_t);
+  const bool zero_copy = out_mem == LK_HOST && seed_rows == 0 && out_s_bytes + out_i_bytes <= (64u << 10);
+  if (zero_copy) {
+    if (out_s_bytes + out_i_bytes > ix->pin_cap) {
+      if (ix->pin) cudaFreeHost(ix->pin);
+      ix->pin = nullptr;
+      ix->pin_cap = 0;
+      LK_CUDA(cudaHostAlloc((void**)&ix->pin, (64u << 10) + 4096, cudaHostAllocMapped | cudaHostAllocPortable));
+      ix->pin_cap = (64u << 10) + 4096;
+    }
+    d_s = reinterpret_cast<float*>(ix->pin);
+    d_i = reinterpret_cast<int64_t*>(ix->pin + out_s_bytes);
+  } else if (out_mem == LK_HOST) {
     if ((rc = ix->out_s.ensure((size_t)b * k * sizeof(float))) != LK_OK) return rc;
     if ((rc = ix->out_i.ensure((size_t)b * k * sizeof(int64_t))) != LK_OK) return rc;
     d_s = ix->out_s.as<float>();
     d_i = ix->out_i.as<int64_t>();
   }
-  const int merge_len = a.ksel > kMaxK ? a.ksel : (k < a.ksel ? k : a.ksel);
-  const int64_t seed_rows = which == LK_KERNEL_UMMA ? umma_seed_rows(a, ix->sm_count) : 0;
   SearchArgs a0 = a;  // the seeding search over a prefix of the corpus
   if (seed_rows > 0) {
     a0.n_rows = seed_rows;
@@ -628,10 +642,16 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   // 5. results (and the kernels' error flag) back to the host
   if (out_mem == LK_HOST) {
     int flag = 0;
-    LK_CUDA(cudaMemcpyAsync(out_scores, d_s, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    LK_CUDA(cudaMemcpyAsync(out_idx, d_i, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (!zero_copy) {
+      LK_CUDA(cudaMemcpyAsync(out_scores, d_s, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LK_CUDA(cudaMemcpyAsync(out_idx, d_i, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
     LK_CUDA(cudaMemcpyAsync(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     LK_CUDA(cudaStreamSynchronize(st));
+    if (zero_copy) {
+      memcpy(out_scores, d_s, (size_t)b * k * sizeof(float));
+      memcpy(out_idx, d_i, (size_t)b * k * sizeof(int64_t));
+    }
     if (flag != 0) {
       cudaMemsetAsync(ix->err_flag, 0, sizeof(int), st);
       set_error("search kernel pipeline timed out (barrier code %d); results are invalid", flag);
