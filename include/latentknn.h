@@ -50,6 +50,9 @@ typedef struct lk_index lk_index;
 typedef struct lk_ae lk_ae;
 typedef struct lk_comm lk_comm;
 
+#define LK_MAX_K 4096           /* largest top-k of lk_index_search / lk_merge_topk */
+#define LK_MAX_K_FUSED 128      /* largest top-k one fused search selects in a single pass; also the
+                                   limit of the peer exchange (lk_comm_*) */
 #define LK_MAX_WORLD 16         /* ranks of one candidate exchange (one NVLink domain) */
 #define LK_IPC_HANDLE_BYTES 64  /* sizeof(cudaIpcMemHandle_t) */
 
@@ -96,7 +99,12 @@ int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host,
  *      FAISSEmbeddingRetriever.search (FAISSEmbeddingRetriever.py:314-326).
  *
  * queries     b x dim row-major, q_dtype/q_mem as above
- * k           1..128; the caller clamps to min(k, rows) like bruteforce.py:81
+ * k           1..LK_MAX_K; the caller clamps to min(k, rows) like bruteforce.py:81.  Up to 128 the
+ *             fused kernel selects in one pass over the corpus.  Above 128 the corpus is cut
+ *             into row slabs, each slab's best 128 come from the same fused kernel and a
+ *             sorting merge folds them into the result; a slab whose 128th best still reaches
+ *             a query's k-th score is split and searched again, down to single 128-row blocks,
+ *             so the result is the exact top-k under (score desc, row asc) for any data.
  * out_scores  b x k float32, best first, higher = better for every metric
  * out_idx     b x k int64 row positions + idx_base (idx_base = first global row of a shard)
  * out_mem     where the two outputs live; for LK_HOST the call returns after the copy
@@ -117,7 +125,8 @@ int lk_index_last_timing(lk_index* ix, float* out_search_kernel_ms, float* out_t
 int lk_index_set_timing(lk_index* ix, int enabled);
 
 /* ---- k-way merge of per-shard candidates (net-new):
- * cand_* are b x n_lists x list_len, index < 0 or NaN score = padding.  Device or host. */
+ * cand_* are b x n_lists x list_len, index < 0 or NaN score = padding.  Device or host.
+ * k <= LK_MAX_K; for k > LK_MAX_K_FUSED at most 16384 candidates per query (n_lists x list_len). */
 int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b,
                   int n_lists, int list_len, int k, float* out_scores, int64_t* out_idx,
                   int mem, void* stream);

@@ -17,7 +17,8 @@ LK_HOST, LK_DEVICE = 0, 1
 LK_COSINE, LK_EUCLIDEAN, LK_MAHALANOBIS = 0, 1, 2
 LK_KERNEL_AUTO, LK_KERNEL_SIMT, LK_KERNEL_UMMA = 0, 1, 2
 LK_AE_DAE, LK_AE_CAE, LK_AE_VAE_MU = 0, 1, 2
-LK_MAX_K = 128
+LK_MAX_K = 4096       # lk_index_search / lk_merge_topk / lk_maxsim_rerank
+LK_MAX_K_FUSED = 128  # one fused pass; above it lk_index_search runs the slab search.  Also the peer exchange's limit
 LK_MAX_WORLD = 16
 LK_IPC_HANDLE_BYTES = 64
 

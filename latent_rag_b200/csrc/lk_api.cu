@@ -128,6 +128,7 @@ struct lk_index {
   unsigned char* pin = nullptr;  // pinned, device-visible host staging of that path: queries | scores | ids
   size_t pin_cap = 0;
   Buf stage, white, q_tiles, q_side, part_s, part_i, part_c, out_s, out_i, debug;
+  Buf deep_s, deep_i, deep_last, deep_flags, deep_tiles, deep_side;  // slab search (k > 128)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float last_search_ms = 0.f, last_total_ms = 0.f;
@@ -173,7 +174,8 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->ticket) cudaFree(ix->ticket);
   if (ix->pin) cudaFreeHost(ix->pin);
   Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->part_c,
-                 &ix->out_s, &ix->out_i, &ix->debug};
+                 &ix->out_s, &ix->out_i, &ix->debug, &ix->deep_s, &ix->deep_i, &ix->deep_last, &ix->deep_flags,
+                 &ix->deep_tiles, &ix->deep_side};
   for (Buf* b : bufs) b->release();
   for (cudaEvent_t e : ix->ev)
     if (e) cudaEventDestroy(e);
@@ -411,6 +413,210 @@ static int pick_kernel(const lk_index* ix, int requested, int k) {
   return requested;
 }
 
+
+// ------------------------------------------------------------------------------------
+// search over a run of rows (the whole corpus, or one slab of a deep search)
+// ------------------------------------------------------------------------------------
+static SearchArgs rows_args(const lk_index* ix, const unsigned char* tiles, const float* side, int64_t n_rows,
+                            const unsigned char* q_tiles, const float* q_side, int64_t b, int k) {
+  SearchArgs a = {};
+  a.tiles = tiles;
+  a.side = side;
+  a.n_rows = n_rows;
+  a.g = ix->g;
+  a.q_tiles = q_tiles;
+  a.q_side = q_side;
+  a.n_queries = b;
+  a.metric = ix->kmetric;
+  a.k = k;
+  a.err_flag = ix->err_flag;
+  return a;
+}
+
+// Plan, fused distance + selection, merge of the partial lists: [b, k] results into d_s / d_i
+// (memory the device can write; ids = row position within the run + idx_base).  The run starts
+// at a 128-row block boundary and covers whole 256-row units unless it ends with the corpus:
+// the kernels score whole units and rely on the NaN side values past the last row.
+// events: record ix->ev[1] / ev[2] around the search kernels.
+static int search_rows(lk_index* ix, int which, SearchArgs a, int64_t idx_base, bool events, const char* dump_path,
+                       float* d_s, int64_t* d_i, cudaStream_t st) {
+  int rc;
+  const int64_t b = a.n_queries;
+  const int k = a.k;
+  a.seed = nullptr;
+  a.debug_tile = nullptr;
+  if (dump_path) {  // bring-up aid: raw accumulator of unit 0 -> file
+    if ((rc = ix->debug.ensure(kBlockRows * kBlockRows * sizeof(float))) != LK_OK) return rc;
+    LK_CUDA(cudaMemsetAsync(ix->debug.p, 0xFF, kBlockRows * kBlockRows * sizeof(float), st));
+    a.debug_tile = ix->debug.as<float>();
+  }
+  if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
+  else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
+  if (rc != LK_OK) return rc;
+  const int merge_len = a.ksel > kMaxK ? a.ksel : (k < a.ksel ? k : a.ksel);
+  const int64_t seed_rows = which == LK_KERNEL_UMMA ? umma_seed_rows(a, ix->sm_count) : 0;
+  SearchArgs a0 = a;  // the seeding search over a prefix of the run
+  if (seed_rows > 0) {
+    a0.n_rows = seed_rows;
+    if ((rc = umma_plan(a0, ix->sm_count, &a0.n_lists, &a0.ksel)) != LK_OK) return rc;
+  }
+  const size_t n_part = (size_t)b * a.n_lists * a.ksel;
+  const size_t n_part0 = seed_rows > 0 ? (size_t)b * a0.n_lists * a0.ksel : 0;
+  const size_t n_part_max = n_part > n_part0 ? n_part : n_part0;
+  if ((rc = ix->part_s.ensure(n_part_max * sizeof(float))) != LK_OK) return rc;
+  if ((rc = ix->part_i.ensure(n_part_max * sizeof(int32_t))) != LK_OK) return rc;
+  a.part_scores = a0.part_scores = ix->part_s.as<float>();
+  a.part_idx = a0.part_idx = ix->part_i.as<int32_t>();
+  a.part_cnt = a0.part_cnt = nullptr;
+  const bool counted = which == LK_KERNEL_UMMA && a.ksel > kMaxK;  // append buffers report their fill
+  const size_t n_cnt = (size_t)b * a.n_lists, n_cnt0 = seed_rows > 0 ? (size_t)b * a0.n_lists : 0;
+  if (counted) {
+    if ((rc = ix->part_c.ensure((n_cnt > n_cnt0 ? n_cnt : n_cnt0) * sizeof(int))) != LK_OK) return rc;
+    a.part_cnt = a0.part_cnt = ix->part_c.as<int>();
+  }
+
+  // fused distance + selection
+  if (events) LK_CUDA(cudaEventRecord(ix->ev[1], st));
+  if (seed_rows > 0) {  // (the tcgen05 kernel marks the list slots it does not own itself)
+    if ((rc = launch_search_umma(a0, ix->sm_count, st)) != LK_OK) return rc;
+    rc = launch_merge_i32(a0.part_scores, a0.part_idx, a0.part_cnt, b, a0.n_lists, merge_len, a0.ksel, k, 0, d_s,
+                          d_i, st);
+    if (rc != LK_OK) return rc;
+    a.seed = d_s;  // read at the start of the main kernel's segments, overwritten by the final merge
+  }
+  if (which != LK_KERNEL_UMMA) {
+    LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
+    LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
+  } else if (const char* e = getenv("LK_DBG")) {
+    if (atoi(e) & 8) {  // test aid: poison what the kernel must not rely on (huge scores, valid-looking ids / counts)
+      LK_CUDA(cudaMemsetAsync(a.part_scores, 0x7F, n_part * sizeof(float), st));
+      LK_CUDA(cudaMemsetAsync(a.part_idx, 0x00, n_part * sizeof(int32_t), st));
+      if (a.part_cnt) LK_CUDA(cudaMemsetAsync(a.part_cnt, 0x01, n_cnt * sizeof(int), st));
+    }
+  }
+  if (which == LK_KERNEL_UMMA) rc = launch_search_umma(a, ix->sm_count, st);
+  else rc = launch_search_simt(a, ix->sm_count, st);
+  if (rc != LK_OK) return rc;
+  if (events) LK_CUDA(cudaEventRecord(ix->ev[2], st));
+
+  if (dump_path) {
+    std::vector<float> tile(kBlockRows * kBlockRows);
+    LK_CUDA(cudaMemcpyAsync(tile.data(), ix->debug.p, tile.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaStreamSynchronize(st));
+    if (FILE* f = fopen(dump_path, "wb")) {
+      fwrite(tile.data(), sizeof(float), tile.size(), f);
+      fclose(f);
+    }
+  }
+
+  // merge the per-CTA lists.  Sorted selectors leave their best k in the first k slots; the
+  // append-buffer selector (ksel > kMaxK) leaves an unordered superset of its best k anywhere
+  // in the slot
+  return launch_merge_i32(a.part_scores, a.part_idx, a.part_cnt, b, a.n_lists, merge_len, a.ksel, k, idx_base, d_s,
+                          d_i, st);
+}
+
+// ------------------------------------------------------------------------------------
+// k > 128: slab search (kernels in lk_deep.cu).  The reference ranks a materialised score
+// matrix and so takes any k (retrieval/bruteforce.py:81-82).  Here the corpus is cut into slabs
+// of whole 256-row units, about twice as many as lists of 128 would hold k; the fused kernel
+// takes every slab's best 128 and a sorting merge folds them into the running result.  A slab
+// with more than 128 rows whose 128th best still reaches some query's k-th score may hide
+// better rows: it is split in two and searched again (the merge first drops what the result
+// holds from those rows), down to single 128-row blocks, which are copied next to a padding
+// block so that the unit-wide kernel sees nothing else.  Exact for any data; one pass over the
+// corpus when the best rows are spread out, O(log) more over the crowded slabs when they are not.
+// ------------------------------------------------------------------------------------
+struct Slab {
+  int64_t row0, rows;
+  bool block;  // one 128-row block, searched through the scratch copy
+};
+
+static int deep_search(lk_index* ix, int which, const unsigned char* q_tiles, const float* q_side, int64_t b, int k,
+                       int64_t idx_base, float* d_s, int64_t* d_i, cudaStream_t st) {
+  constexpr int64_t kUnit = 2 * kBlockRows;
+  int rc;
+  const int64_t n = ix->n_rows, n_units = (n + kUnit - 1) / kUnit;
+  const int64_t block_bytes = ix->g.block_bytes();
+  int64_t want = 2 * ((k + kMaxK - 1) / kMaxK);
+  if (want > n_units) want = n_units;
+  const int64_t upu = (n_units + want - 1) / want;  // units per slab
+  std::vector<Slab> work, next;
+  for (int64_t u = 0; u < n_units; u += upu) {
+    const int64_t row0 = u * kUnit, rows = n - row0 < upu * kUnit ? n - row0 : upu * kUnit;
+    work.push_back({row0, rows, false});
+  }
+  const int cap = deep_merge_capacity(k, 1, kMaxK);
+  std::vector<int> flags;
+  bool have_res = false;
+  while (!work.empty()) {
+    const int64_t n_round = (int64_t)work.size();
+    const int64_t per = n_round < cap ? n_round : cap;  // slabs per merge launch
+    if ((rc = ix->deep_s.ensure((size_t)per * b * kMaxK * sizeof(float))) != LK_OK) return rc;
+    if ((rc = ix->deep_i.ensure((size_t)per * b * kMaxK * sizeof(int64_t))) != LK_OK) return rc;
+    if ((rc = ix->deep_last.ensure((size_t)n_round * b * sizeof(float))) != LK_OK) return rc;
+    if ((rc = ix->deep_flags.ensure((size_t)n_round * sizeof(int))) != LK_OK) return rc;
+    LK_CUDA(cudaMemsetAsync(ix->deep_flags.p, 0, (size_t)n_round * sizeof(int), st));
+    for (int64_t g0 = 0; g0 < n_round; g0 += per) {
+      const int64_t g1 = g0 + per < n_round ? g0 + per : n_round;
+      DeepLists L = {};
+      L.n_lists = L.n_ranges = (int)(g1 - g0);
+      L.len = kMaxK;
+      L.list_stride = b * kMaxK;
+      L.query_stride = kMaxK;
+      for (int64_t g = g0; g < g1; ++g) {
+        const Slab& s = work[(size_t)g];
+        const unsigned char* tiles = ix->tiles + (s.row0 / kBlockRows) * block_bytes;
+        const float* side = ix->side + s.row0;
+        if (s.block) {  // [the block][a padding block: zero rows, NaN side values]
+          if (ix->deep_tiles.p == nullptr) {
+            if ((rc = ix->deep_tiles.ensure((size_t)2 * block_bytes)) != LK_OK) return rc;
+            if ((rc = ix->deep_side.ensure((size_t)kUnit * sizeof(float))) != LK_OK) return rc;
+            LK_CUDA(cudaMemsetAsync(ix->deep_tiles.p, 0, (size_t)2 * block_bytes, st));
+            LK_CUDA(cudaMemsetAsync(ix->deep_side.p, 0xFF, (size_t)kUnit * sizeof(float), st));
+          }
+          LK_CUDA(cudaMemcpyAsync(ix->deep_tiles.p, tiles, (size_t)block_bytes, cudaMemcpyDeviceToDevice, st));
+          LK_CUDA(cudaMemcpyAsync(ix->deep_side.p, side, kBlockRows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+          tiles = ix->deep_tiles.as<unsigned char>();
+          side = ix->deep_side.as<float>();
+        }
+        const SearchArgs a = rows_args(ix, tiles, side, s.rows, q_tiles, q_side, b, kMaxK);
+        const size_t o = (size_t)(g - g0) * b * kMaxK;
+        rc = search_rows(ix, which, a, idx_base + s.row0, false, nullptr, ix->deep_s.as<float>() + o,
+                         ix->deep_i.as<int64_t>() + o, st);
+        if (rc != LK_OK) return rc;
+        L.lo[g - g0] = idx_base + s.row0;
+        L.hi[g - g0] = idx_base + s.row0 + s.rows;
+      }
+      rc = launch_deep_merge(ix->deep_s.as<float>(), ix->deep_i.as<int64_t>(), L, b, k, have_res, d_s, d_i,
+                             ix->deep_last.as<float>() + g0 * b, st);
+      if (rc != LK_OK) return rc;
+      have_res = true;
+    }
+    rc = launch_deep_saturated(ix->deep_last.as<float>(), (int)n_round, b, d_s, k, ix->deep_flags.as<int>(), st);
+    if (rc != LK_OK) return rc;
+    flags.resize((size_t)n_round);
+    LK_CUDA(cudaMemcpyAsync(flags.data(), ix->deep_flags.p, (size_t)n_round * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LK_CUDA(cudaStreamSynchronize(st));
+    next.clear();
+    for (int64_t g = 0; g < n_round; ++g) {
+      if (!flags[(size_t)g]) continue;
+      const Slab& s = work[(size_t)g];
+      const int64_t units = (s.rows + kUnit - 1) / kUnit;
+      if (units >= 2) {
+        const int64_t h = (units + 1) / 2 * kUnit;
+        next.push_back({s.row0, h, false});
+        next.push_back({s.row0 + h, s.rows - h, false});
+      } else if (!s.block && s.rows > kBlockRows) {
+        next.push_back({s.row0, kBlockRows, true});
+        next.push_back({s.row0 + kBlockRows, s.rows - kBlockRows, true});
+      }
+    }
+    work.swap(next);
+  }
+  return LK_OK;
+}
+
 int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, int64_t b, int k,
                     float* out_scores, int64_t* out_idx, int out_mem, int64_t idx_base, int kernel,
                     void* stream) {
@@ -420,8 +626,8 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     set_error("lk_index_search: bad argument");
     return LK_ERR_INVALID;
   }
-  if (k < 1 || k > kMaxK) {
-    set_error("lk_index_search: k=%d outside 1..%d", k, kMaxK);
+  if (k < 1 || k > kDeepMaxK) {
+    set_error("lk_index_search: k=%d outside 1..%d", k, kDeepMaxK);
     return LK_ERR_INVALID;
   }
   if (ix->n_rows < 1) {
@@ -429,8 +635,9 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     return LK_ERR_INVALID;
   }
   if (b == 0) return LK_OK;
-  const int which = pick_kernel(ix, kernel, k);
-  if (which == LK_KERNEL_UMMA && !umma_supported(ix->g, k)) {
+  const bool deep = k > kMaxK;  // slab search: every fused search below asks for kMaxK
+  const int which = pick_kernel(ix, kernel, deep ? kMaxK : k);
+  if (which == LK_KERNEL_UMMA && !umma_supported(ix->g, deep ? kMaxK : k)) {
     set_error("lk_index_search: the tcgen05 kernel needs bf16 storage (k=%d, storage=%d)", k,
               ix->storage);
     return LK_ERR_UNSUPPORTED;
@@ -529,38 +736,18 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   rc = ingest_rows(ix, queries, q_dtype, q_mem, b, ix->q_tiles.p, ix->q_side.as<float>(), 0, st);
   if (rc != LK_OK) return rc;
 
-  // 2. plan + partial lists
-  SearchArgs a = {};
-  a.tiles = ix->tiles;
-  a.side = ix->side;
-  a.n_rows = ix->n_rows;
-  a.g = ix->g;
-  a.q_tiles = ix->q_tiles.p;
-  a.q_side = ix->q_side.as<float>();
-  a.n_queries = b;
-  a.metric = ix->kmetric;
-  a.k = k;
-  a.err_flag = ix->err_flag;
-  a.seed = nullptr;
-  a.debug_tile = nullptr;
-  const char* dump_path = which == LK_KERNEL_UMMA ? getenv("LK_UMMA_DUMP") : nullptr;
-  if (dump_path) {  // bring-up aid: raw accumulator of unit 0 -> file
-    if ((rc = ix->debug.ensure(kBlockRows * kBlockRows * sizeof(float))) != LK_OK) return rc;
-    LK_CUDA(cudaMemsetAsync(ix->debug.p, 0xFF, kBlockRows * kBlockRows * sizeof(float), st));
-    a.debug_tile = ix->debug.as<float>();
-  }
-  if (which == LK_KERNEL_UMMA) rc = umma_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
-  else rc = simt_plan(a, ix->sm_count, &a.n_lists, &a.ksel);
-  if (rc != LK_OK) return rc;
-  const int merge_len = a.ksel > kMaxK ? a.ksel : (k < a.ksel ? k : a.ksel);
-  const int64_t seed_rows = which == LK_KERNEL_UMMA ? umma_seed_rows(a, ix->sm_count) : 0;
+  // 2.-4. plan, fused distance + selection, merge of the partial lists
+  const SearchArgs a = rows_args(ix, ix->tiles, ix->side, ix->n_rows, ix->q_tiles.as<unsigned char>(),
+                                 ix->q_side.as<float>(), b, k);
+  const char* dump_path = which == LK_KERNEL_UMMA && !deep ? getenv("LK_UMMA_DUMP") : nullptr;
+  const int64_t seed_rows = which == LK_KERNEL_UMMA && !deep ? umma_seed_rows(a, ix->sm_count) : 0;
   // results land here: the caller's device buffers; for host outputs a device staging buffer, or --
   // small results that no later kernel reads back -- the pinned block, written by the merge kernel
   // itself (zero copy: two device-to-host copies less per call)
   float* d_s = out_scores;
   int64_t* d_i = out_idx;
   const size_t out_s_bytes = ((size_t)b * k * sizeof(float) + 15) / 16 * 16, out_i_bytes = (size_t)b * k * sizeof(int64_t);
-  const bool zero_copy = out_mem == LK_HOST && seed_rows == 0 && out_s_bytes + out_i_bytes <= (64u << 10);
+  const bool zero_copy = out_mem == LK_HOST && !deep && seed_rows == 0 && out_s_bytes + out_i_bytes <= (64u << 10);
   if (zero_copy) {
     if (out_s_bytes + out_i_bytes > ix->pin_cap) {
       if (ix->pin) cudaFreeHost(ix->pin);
@@ -577,66 +764,20 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     d_s = ix->out_s.as<float>();
     d_i = ix->out_i.as<int64_t>();
   }
-  SearchArgs a0 = a;  // the seeding search over a prefix of the corpus
-  if (seed_rows > 0) {
-    a0.n_rows = seed_rows;
-    if ((rc = umma_plan(a0, ix->sm_count, &a0.n_lists, &a0.ksel)) != LK_OK) return rc;
-  }
-  const size_t n_part = (size_t)b * a.n_lists * a.ksel;
-  const size_t n_part0 = seed_rows > 0 ? (size_t)b * a0.n_lists * a0.ksel : 0;
-  const size_t n_part_max = n_part > n_part0 ? n_part : n_part0;
-  if ((rc = ix->part_s.ensure(n_part_max * sizeof(float))) != LK_OK) return rc;
-  if ((rc = ix->part_i.ensure(n_part_max * sizeof(int32_t))) != LK_OK) return rc;
-  a.part_scores = a0.part_scores = ix->part_s.as<float>();
-  a.part_idx = a0.part_idx = ix->part_i.as<int32_t>();
-  a.part_cnt = a0.part_cnt = nullptr;
-  const bool counted = which == LK_KERNEL_UMMA && a.ksel > kMaxK;  // append buffers report their fill
-  const size_t n_cnt = (size_t)b * a.n_lists, n_cnt0 = seed_rows > 0 ? (size_t)b * a0.n_lists : 0;
-  if (counted) {
-    if ((rc = ix->part_c.ensure((n_cnt > n_cnt0 ? n_cnt : n_cnt0) * sizeof(int))) != LK_OK) return rc;
-    a.part_cnt = a0.part_cnt = ix->part_c.as<int>();
-  }
-
-  // 3. fused distance + selection
-  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
-  if (seed_rows > 0) {  // (the tcgen05 kernel marks the list slots it does not own itself)
-    if ((rc = launch_search_umma(a0, ix->sm_count, st)) != LK_OK) return rc;
-    rc = launch_merge_i32(a0.part_scores, a0.part_idx, a0.part_cnt, b, a0.n_lists, merge_len, a0.ksel, k, 0, d_s,
-                          d_i, st);
-    if (rc != LK_OK) return rc;
-    a.seed = d_s;  // read at the start of the main kernel's segments, overwritten by the final merge
-  }
-  if (which != LK_KERNEL_UMMA) {
-    LK_CUDA(cudaMemsetAsync(a.part_scores, 0xFF, n_part * sizeof(float), st));   // NaN = empty slot
-    LK_CUDA(cudaMemsetAsync(a.part_idx, 0xFF, n_part * sizeof(int32_t), st));    // -1
-  } else if (const char* e = getenv("LK_DBG")) {
-    if (atoi(e) & 8) {  // test aid: poison what the kernel must not rely on (huge scores, valid-looking ids / counts)
-      LK_CUDA(cudaMemsetAsync(a.part_scores, 0x7F, n_part * sizeof(float), st));
-      LK_CUDA(cudaMemsetAsync(a.part_idx, 0x00, n_part * sizeof(int32_t), st));
-      if (a.part_cnt) LK_CUDA(cudaMemsetAsync(a.part_cnt, 0x01, n_cnt * sizeof(int), st));
+  if (!deep) {
+    if ((rc = search_rows(ix, which, a, idx_base, ix->timing, dump_path, d_s, d_i, st)) != LK_OK) return rc;
+  } else {
+    // a chunk of queries at a time: every slab of a merge launch keeps 128 candidates per query
+    constexpr int64_t kDeepChunk = 512;
+    if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
+    for (int64_t q0 = 0; q0 < b; q0 += kDeepChunk) {
+      const int64_t bc = b - q0 < kDeepChunk ? b - q0 : kDeepChunk;
+      rc = deep_search(ix, which, ix->q_tiles.as<unsigned char>() + (q0 / kBlockRows) * ix->g.block_bytes(),
+                       ix->q_side.as<float>() + q0, bc, k, idx_base, d_s + q0 * k, d_i + q0 * k, st);
+      if (rc != LK_OK) return rc;
     }
+    if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[2], st));
   }
-  if (which == LK_KERNEL_UMMA) rc = launch_search_umma(a, ix->sm_count, st);
-  else rc = launch_search_simt(a, ix->sm_count, st);
-  if (rc != LK_OK) return rc;
-  if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[2], st));
-
-  if (dump_path) {
-    std::vector<float> tile(kBlockRows * kBlockRows);
-    LK_CUDA(cudaMemcpyAsync(tile.data(), ix->debug.p, tile.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
-    LK_CUDA(cudaStreamSynchronize(st));
-    if (FILE* f = fopen(dump_path, "wb")) {
-      fwrite(tile.data(), sizeof(float), tile.size(), f);
-      fclose(f);
-    }
-  }
-
-  // 4. merge the per-CTA lists.  Sorted selectors leave their best k in the first k slots; the
-  // append-buffer selector (ksel > kMaxK) leaves an unordered superset of its best k anywhere
-  // in the slot
-  rc = launch_merge_i32(a.part_scores, a.part_idx, a.part_cnt, b, a.n_lists, merge_len, a.ksel, k, idx_base, d_s, d_i,
-                        st);
-  if (rc != LK_OK) return rc;
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[3], st));
 
   // 5. results (and the kernels' error flag) back to the host
@@ -680,18 +821,33 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
 // ------------------------------------------------------------------------------------
 int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b, int n_lists,
                   int list_len, int k, float* out_scores, int64_t* out_idx, int mem, void* stream) {
-  if (b < 0 || n_lists < 1 || list_len < 1 || k < 1 || k > kMaxK || (mem != LK_HOST && mem != LK_DEVICE) ||
+  if (b < 0 || n_lists < 1 || list_len < 1 || k < 1 || k > kDeepMaxK || (mem != LK_HOST && mem != LK_DEVICE) ||
       (b > 0 && (!cand_scores || !cand_idx || !out_scores || !out_idx))) {
     set_error("lk_merge_topk: bad argument");
     return LK_ERR_INVALID;
   }
+  if (k > kMaxK && (int64_t)n_lists * list_len > kDeepMaxCand) {
+    set_error("lk_merge_topk: k=%d > %d takes at most %d candidates per query (%d lists of %d given)", k, kMaxK,
+              kDeepMaxCand, n_lists, list_len);
+    return LK_ERR_UNSUPPORTED;
+  }
   if (b == 0) return LK_OK;
+  // up to kMaxK: insertion / selection merge; above: the sorting merge of the slab search
+  auto merge = [&](const float* cs, const int64_t* ci, float* os, int64_t* oi, cudaStream_t st) {
+    if (k <= kMaxK) return launch_merge_i64(cs, ci, b, n_lists, list_len, k, os, oi, st);
+    DeepLists L = {};
+    L.n_lists = n_lists;
+    L.len = list_len;
+    L.list_stride = list_len;
+    L.query_stride = (int64_t)n_lists * list_len;
+    return launch_deep_merge(cs, ci, L, b, k, 0, os, oi, nullptr, st);
+  };
   int sm = 0;
   int rc = check_device(device, &sm);
   if (rc != LK_OK) return rc;
   DeviceGuard guard(device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mem == LK_DEVICE) return launch_merge_i64(cand_scores, cand_idx, b, n_lists, list_len, k, out_scores, out_idx, st);
+  if (mem == LK_DEVICE) return merge(cand_scores, cand_idx, out_scores, out_idx, st);
   const size_t nc = (size_t)b * n_lists * list_len, no = (size_t)b * k;
   Buf cs, ci, os, oi;
   auto done = [&](int code) {
@@ -705,8 +861,7 @@ int lk_merge_topk(int device, const float* cand_scores, const int64_t* cand_idx,
   if ((e = cudaMemcpyAsync(cs.p, cand_scores, nc * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
       (e = cudaMemcpyAsync(ci.p, cand_idx, nc * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
     return done(cuda_fail(e, "cudaMemcpyAsync(H2D)", __FILE__, __LINE__));
-  rc = launch_merge_i64(cs.as<float>(), ci.as<int64_t>(), b, n_lists, list_len, k, os.as<float>(),
-                        oi.as<int64_t>(), st);
+  rc = merge(cs.as<float>(), ci.as<int64_t>(), os.as<float>(), oi.as<int64_t>(), st);
   if (rc != LK_OK) return done(rc);
   if ((e = cudaMemcpyAsync(out_scores, os.p, no * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
       (e = cudaMemcpyAsync(out_idx, oi.p, no * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||

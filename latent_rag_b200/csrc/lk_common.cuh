@@ -29,7 +29,10 @@ constexpr int kBlockRows = 128;       // rows per row block (= UMMA M / N granul
 constexpr int kChunkBytes = 16;       // one K chunk of one row
 constexpr int kRowBytes = 128;        // bytes of one row inside a K block (swizzle span)
 constexpr int kSlabBytes = kBlockRows * kRowBytes;  // 16384
-constexpr int kMaxK = 128;            // largest supported top-k
+constexpr int kMaxK = 128;            // largest top-k of one fused search (entries per selector list)
+constexpr int kDeepMaxK = LK_MAX_K;   // largest top-k of a slab search (lk_deep.cu)
+constexpr int kDeepMaxLists = 96;     // slab lists folded in by one deep merge launch
+constexpr int kDeepMaxCand = 16384;   // entries one deep merge sorts in shared memory (192 KB)
 constexpr int kSimtQG = 4;            // queries per CTA pass in the SIMT kernel
 
 // byte offset of logical chunk c (0..7) of row r inside a slab
@@ -134,6 +137,26 @@ int launch_merge_i32(const float* ps, const int32_t* pi, const int* pc, int64_t 
                      int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st);
 int launch_merge_i64(const float* ps, const int64_t* pi, int64_t b, int n_lists, int list_len, int k,
                      float* out_s, int64_t* out_i, cudaStream_t st);
+
+// Slab search for k > kMaxK (lk_deep.cu).  List l of query q starts at l * list_stride +
+// q * query_stride of the candidate arrays (int64 ids, < 0 or NaN score = empty).  Entries of the
+// running result whose id falls in [lo[r], hi[r]) are dropped before the merge: the incoming
+// lists supply those rows again (a split slab is searched a second time, half by half).
+struct DeepLists {
+  int n_lists, len, n_ranges;
+  int64_t list_stride, query_stride;
+  int64_t lo[kDeepMaxLists], hi[kDeepMaxLists];
+};
+// lists of `list_len` entries one launch can take next to a running result of k entries
+int deep_merge_capacity(int k, int have_res, int list_len);
+// res (b x k, in place; read only if have_res) <- best k of res + lists.  list_last: optional
+// [n_lists, b]; receives each list's last score when its slab (hi - lo rows) holds more rows
+// than the list, NaN otherwise.
+int launch_deep_merge(const float* cs, const int64_t* ci, const DeepLists& L, int64_t b, int k, int have_res,
+                      float* res_s, int64_t* res_i, float* list_last, cudaStream_t st);
+// flags[l] = 1 if for some query list l's last score reaches the query's k-th best
+int launch_deep_saturated(const float* list_last, int n_lists, int64_t b, const float* res_s, int k, int* flags,
+                          cudaStream_t st);
 
 int launch_ae_encode(const float* x, int64_t m, int d_in, int d_hidden, int d_latent, const float* w0t,
                      const float* b0, const float* w1t, const float* b1, int l2norm, float* z,

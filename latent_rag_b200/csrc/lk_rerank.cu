@@ -13,15 +13,16 @@ namespace {
 
 constexpr int kRerankWarps = 4;
 
+// one warp per query; blockDim.x / 32 queries per CTA, cand_k doc ids per warp in dynamic shared memory
 __global__ void __launch_bounds__(kRerankWarps * 32) maxsim_rerank_kernel(
     const float* __restrict__ scores, const int64_t* __restrict__ idx, int64_t b, int cand_k,
     const int64_t* __restrict__ row_doc, int64_t n_rows, int top_k, float* __restrict__ out_s,
     int64_t* __restrict__ out_doc) {
-  __shared__ int64_t s_doc[kRerankWarps][kMaxK];
+  extern __shared__ int64_t s_doc[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q = (int64_t)blockIdx.x * kRerankWarps + warp;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (q >= b) return;
-  int64_t* doc = s_doc[warp];
+  int64_t* doc = s_doc + (size_t)warp * cand_k;
   for (int j = lane; j < cand_k; j += 32) {
     const int64_t r = idx[q * cand_k + j];
     doc[j] = (r >= 0 && r < n_rows) ? row_doc[r] : INT64_MIN;  // INT64_MIN = not a candidate
@@ -59,7 +60,7 @@ using namespace lk;
 extern "C" int lk_maxsim_rerank(int device, const float* cand_scores, const int64_t* cand_idx, int64_t b, int cand_k,
                                 const int64_t* row_doc_ids, int64_t n_rows, int top_k, float* out_scores,
                                 int64_t* out_doc_ids, void* stream) {
-  if (b < 0 || cand_k < 1 || cand_k > kMaxK || top_k < 1 || top_k > cand_k || n_rows < 0 ||
+  if (b < 0 || cand_k < 1 || cand_k > kDeepMaxK || top_k < 1 || top_k > cand_k || n_rows < 0 ||
       (b > 0 && (!cand_scores || !cand_idx || !row_doc_ids || !out_scores || !out_doc_ids))) {
     set_error("lk_maxsim_rerank: bad argument");
     return LK_ERR_INVALID;
@@ -75,8 +76,9 @@ extern "C" int lk_maxsim_rerank(int device, const float* cand_scores, const int6
   int prev = -1;
   cudaGetDevice(&prev);
   LK_CUDA(cudaSetDevice(device));
-  const unsigned grid = (unsigned)((b + kRerankWarps - 1) / kRerankWarps);
-  maxsim_rerank_kernel<<<grid, kRerankWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int warps = cand_k <= 1024 ? kRerankWarps : 1;  // at most 32 KB of doc ids per CTA
+  const unsigned grid = (unsigned)((b + warps - 1) / warps);
+  maxsim_rerank_kernel<<<grid, warps * 32, (size_t)warps * cand_k * sizeof(int64_t), static_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_idx, b, cand_k, row_doc_ids, n_rows, top_k, out_scores, out_doc_ids);
   cudaError_t le = cudaGetLastError();
   if (prev >= 0) cudaSetDevice(prev);

@@ -15,7 +15,7 @@ from . import _native as nat
 
 
 class PeerExchange:
-    def __init__(self, device: int, rank: int, world: int, max_b: int = 4096, max_k: int = nat.LK_MAX_K):
+    def __init__(self, device: int, rank: int, world: int, max_b: int = 4096, max_k: int = nat.LK_MAX_K_FUSED):
         self._lib = nat.load()
         nat.require_device()
         self.device, self.rank, self.world = int(device), int(rank), int(world)

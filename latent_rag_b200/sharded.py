@@ -148,9 +148,11 @@ class ShardedRetriever:
             queries = queries.unsqueeze(0)
         b = queries.size(0)
         k = min(int(k), self.n_total)
+        # the peer exchange carries up to 128 candidates per rank; deeper results take the all-gather
+        xchg = self._xchg if self._xchg is not None and k <= self._xchg.max_k else None
         # 1. local top-k with global ids, padded to k when the shard is smaller than k
         kl = min(k, self.n_local)
-        if kl == k and b > 0 and self._xchg is not None:
+        if kl == k and b > 0 and xchg is not None:
             d, i = self._local_search(queries, k)
         else:
             d = torch.full((b, k), float("-inf"), dtype=torch.float32, device=self.comm_device)
@@ -160,8 +162,8 @@ class ShardedRetriever:
                 d[:, :kl] = torch.as_tensor(dl, device=self.comm_device)
                 i[:, :kl] = torch.as_tensor(il, device=self.comm_device)
         # 2+3 fused: candidates go straight into every peer's buffer, flags, wait, merge
-        if self._xchg is not None:
-            return self._xchg.exchange_merge(d, i, k)
+        if xchg is not None:
+            return xchg.exchange_merge(d, i, k)
         # 2. the one exchange step: all-gather of the candidates
         if self.world > 1:
             gd = torch.empty((self.world * b, k), dtype=torch.float32, device=self.comm_device)

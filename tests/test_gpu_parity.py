@@ -241,6 +241,160 @@ def test_ties_resolve_to_the_lowest_index(lrb, kernel, k, monkeypatch):
     _assert_topk(d_ref, i_ref, d, i, l2=(emb, base[:20]))
 
 
+# ---------------------------------------------------------------------------------------
+# k > 128: slab search (the reference takes any k: k = min(k, N), bruteforce.py:81-82)
+# ---------------------------------------------------------------------------------------
+DEEP_SHAPES = [
+    # n, b, dim, k
+    (3000, 40, 64, 129),
+    (20000, 70, 384, 200),
+    (300, 3, 32, 300),       # k = N: every unit is split down to its blocks
+    (1000, 5, 64, 1000),
+    (700, 2, 48, 5000),      # clamps to N
+    (50000, 600, 64, 500),   # more than one chunk of queries
+    (100000, 9, 128, 4096),
+    (5000, 2, 768, 4096),
+]
+
+
+@pytest.mark.parametrize("n,b,dim,k", DEEP_SHAPES)
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_deep_k_matches_oracle(lrb, n, b, dim, k, metric):
+    rng = np.random.default_rng(n + b + k)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric)
+    d, i = r.search(q, k)
+    kk = min(k, n)
+    assert d.shape == (b, kk) and i.shape == (b, kk)
+    d_ref, i_ref = _oracle(emb, q, k, metric)
+    _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
+    assert all(len(set(row.tolist())) == kk for row in i)
+    # device-resident queries and results, global ids of a shard
+    dd, di = r.index.search(q.cuda(), kk, idx_base=7_000_000_000, device_out=True)
+    r.index.check()
+    np.testing.assert_array_equal(di.cpu().numpy() - 7_000_000_000, i)
+    np.testing.assert_array_equal(dd.cpu().numpy(), d)
+
+
+@pytest.mark.parametrize("precision,kernel", [("fp32", "simt"), ("bf16", "simt"), ("bf16", "umma")])
+def test_deep_k_on_every_kernel_with_dirty_workspaces(lrb, precision, kernel, monkeypatch):
+    monkeypatch.setenv("LK_FORCE_KERNEL", kernel)
+    monkeypatch.setenv("LK_DBG", "8")
+    rng = np.random.default_rng(5)
+    n, b, dim, k = 9000, 33, 100, 333
+    emb = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32))
+    if precision == "bf16":
+        emb, q = oracle.bf16_round(emb), oracle.bf16_round(q)
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric="euclidean", precision=precision)
+    for _ in range(2):
+        d, i = r.search(q, k)
+        d_ref, i_ref = _oracle(emb, q, k, "euclidean")
+        _assert_topk(d_ref, i_ref, d, i, l2=(emb, q))
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_deep_k_with_the_best_rows_crowded_into_one_slab(lrb, metric):
+    """Chunks of one document sit next to each other in the corpus: here 400 adjacent rows are
+    all close to the query, so their slab's 128 candidates cannot cover the top 300 and the slab
+    is split and searched again, down to single blocks."""
+    rng = np.random.default_rng(77)
+    n, dim, k = 20000, 64, 300
+    emb = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((3, dim)).astype(np.float32))
+    emb[1000:1400] = q[0] + 0.05 * emb[1000:1400]
+    emb[19900:20000] = q[1] + 0.05 * emb[19900:20000]   # the ragged last unit
+    emb[5000:5200] = q[1] + 0.05 * emb[5000:5200]
+    emb, q = oracle.bf16_round(emb), oracle.bf16_round(q)
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric)
+    d, i = r.search(q, k)
+    assert set(i[0].tolist()) <= set(range(1000, 1400))
+    assert set(i[1].tolist()) == set(range(19900, 20000)) | set(range(5000, 5200))
+    d_ref, i_ref = _oracle(emb, q, k, metric)
+    _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
+
+
+def test_deep_k_ties_resolve_to_the_lowest_index(lrb):
+    """(score desc, index asc) also holds across slabs: 1500 identical rows tie at the top and the
+    first 300 of them are the answer; triplicated rows come out as ascending triples."""
+    rng = np.random.default_rng(3)
+    dup = oracle.bf16_round(torch.from_numpy(rng.standard_normal((1, 64)).astype(np.float32)))
+    rest = oracle.bf16_round(torch.from_numpy(rng.standard_normal((500, 64)).astype(np.float32)))
+    emb = torch.cat([dup.expand(1500, 64), rest])
+    r = lrb.BruteForceRetriever(emb, [""] * 2000, None, metric="cosine")
+    d, i = r.search(dup, 300)
+    assert i[0].tolist() == list(range(300))
+    assert (d[0] == d[0, 0]).all()
+    base = oracle.bf16_round(torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32)))
+    emb = torch.cat([base, base, base])
+    r = lrb.BruteForceRetriever(emb, [""] * 900, None, metric="euclidean")
+    d, i = r.search(base[:20], 600)
+    for row in range(20):
+        assert i[row, :3].tolist() == [row, row + 300, row + 600]
+        for t in range(0, 600, 3):
+            assert d[row, t] == d[row, t + 1] == d[row, t + 2]
+            assert i[row, t] + 300 == i[row, t + 1] and i[row, t] + 600 == i[row, t + 2]
+    d_ref, i_ref = _oracle(emb, base[:20], 600, "euclidean")
+    _assert_topk(d_ref, i_ref, d, i, l2=(emb, base[:20]))
+
+
+def test_deep_k_through_the_other_entry_points(lrb):
+    """FAISS mirror (k > N pads with -1 like upstream), ShardedRetriever (one shard), k past the limit."""
+    rng = np.random.default_rng(9)
+    n, dim = 4000, 64
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(torch.from_numpy(rng.standard_normal((6, dim)).astype(np.float32)))
+    br = lrb.BruteForceRetriever(emb, [""] * n, None, metric="cosine")
+    d0, i0 = br.search(q, 250)
+    fr = lrb.FAISSEmbeddingRetriever(dim, index_type="flatip")
+    fr.build(emb, [""] * n)
+    d1, i1 = fr.search(q, 250)
+    _assert_topk(d0, i0, d1, i1)
+    sr = lrb.ShardedRetriever(emb, 0, "cosine")
+    d2, i2 = sr.search(q, 250)
+    np.testing.assert_array_equal(i2, i0)
+    np.testing.assert_array_equal(d2, d0)
+    texts, scores, ids = br.retrieve(q[0], top_k=250)
+    assert ids == i0[0].tolist() and len(texts) == 250
+    with pytest.raises(ValueError):
+        br.index.search(q, lrb._native.LK_MAX_K + 1)
+
+
+def test_deep_merge_kernel_matches_oracle(lrb):
+    rng = np.random.default_rng(14)
+    for b, lists, ln, k in [(3, 8, 512, 300), (2, 4, 4096, 4096), (5, 100, 128, 1000), (1, 2, 100, 150), (40, 8, 200, 129)]:
+        cd = rng.standard_normal((b, lists, ln)).astype(np.float32)
+        ci = rng.permutation(b * lists * ln).reshape(b, lists, ln).astype(np.int64) + 5_000_000_000
+        ci[:, -1, -2:] = -1  # padding
+        cd[0, 0, :2] = cd[0, 1, 0]  # ties
+        kk = min(k, lists * ln - 2)
+        d, i = lrb.merge_topk(cd, ci, kk)
+        d_ref, i_ref = oracle.merge_topk(cd, ci, kk)
+        np.testing.assert_array_equal(i, i_ref)
+        np.testing.assert_array_equal(d, d_ref)
+        dg, ig = lrb.merge_topk(torch.from_numpy(cd).cuda(), torch.from_numpy(ci).cuda(), kk)
+        np.testing.assert_array_equal(ig.cpu().numpy(), i_ref)
+    with pytest.raises(lrb._native.NativeError):  # more candidates per query than the sorting merge holds
+        lrb.merge_topk(np.zeros((1, 200, 128), np.float32), np.zeros((1, 200, 128), np.int64), 200)
+
+
+def test_retrieve_batch_with_deep_candidates(lrb):
+    """candidate_k = 3 * top_k (main.py:265) above 128."""
+    rng = np.random.default_rng(22)
+    n, dim, b, top_k = 8000, 64, 20, 60
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)))
+    q = oracle.bf16_round(emb[rng.integers(0, n, b)] + 0.3 * torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32)))
+    doc_ids = (rng.permutation(n) // 4).tolist()
+    r = lrb.BruteForceRetriever(emb, [""] * n, doc_ids, metric="cosine")
+    got_ids, got_sc = r.retrieve_batch(q, top_k=top_k, candidate_k=3 * top_k)
+    for row in range(b):
+        _, scores_k, docids_k = r.retrieve(q[row], top_k=3 * top_k)
+        want, want_sc = oracle.maxsim_rerank(scores_k, docids_k, top_k)
+        assert got_ids[row] == want
+        np.testing.assert_allclose(got_sc[row], want_sc, rtol=1e-6)
+
+
 def test_metrics_identical_to_oracle_results(lrb):
     """north_star: identical Recall@k, MRR and nDCG."""
     emb, q = inputs.mid_case_inputs()
