@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-to-peer kernel, or NCCL all-gather + merge")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample-queries", type=int, default=256)
+    ap.add_argument("--cpu-sample-queries", type=int, default=1024)
     return ap.parse_args()
 
 
