@@ -49,6 +49,7 @@ typedef enum lk_ae_kind { LK_AE_DAE = 0, LK_AE_CAE = 1, LK_AE_VAE_MU = 2 } lk_ae
 typedef struct lk_index lk_index;
 typedef struct lk_ae lk_ae;
 typedef struct lk_comm lk_comm;
+typedef struct lk_bert lk_bert;
 
 #define LK_MAX_K 4096           /* largest top-k of lk_index_search / lk_merge_topk */
 #define LK_MAX_K_FUSED 128      /* largest top-k one fused search selects in a single pass; also the
@@ -208,6 +209,47 @@ int lk_ae_set_precision(lk_ae* ae, int precision);
 /* x: m x d_in fp32 row-major; z: m x d_latent fp32 row-major */
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream);
 int lk_ae_destroy(lk_ae* ae);
+
+/* ---- sentence encoder forward: replaces SentenceTransformer("all-MiniLM-L6-v2").encode as the
+ *      reference calls it (retrieval/embedder.py:35-40: convert_to_tensor, normalize_embeddings=True)
+ *      from the token ids on: BERT embeddings + LayerNorm, n_layers x (self-attention, output
+ *      projection + residual + LayerNorm, GELU feed-forward + residual + LayerNorm), masked mean
+ *      pooling, L2 normalisation.  Tokenisation (WordPiece, third-party vocabulary) stays on the
+ *      host.  Weights are the tensors of a transformers BertModel state_dict, fp32 HOST, nn.Linear
+ *      layout [out, in].  The kernels implement head dimension 32 (hidden = 32 x heads), hidden and
+ *      ffn multiples of 128, hidden <= 1024: all-MiniLM-L6-v2 is hidden 384, 12 heads, ffn 1536, 6
+ *      layers, 512 positions, eps 1e-12. */
+typedef struct lk_bert_layer_weights {
+  const float *wq, *bq, *wk, *bk, *wv, *bv; /* attention.self.{query,key,value}.{weight,bias}          */
+  const float *wo, *bo, *ln1_g, *ln1_b;     /* attention.output.dense, attention.output.LayerNorm      */
+  const float *w1, *b1;                     /* intermediate.dense [ffn x hidden]                       */
+  const float *w2, *b2, *ln2_g, *ln2_b;     /* output.dense [hidden x ffn], output.LayerNorm           */
+} lk_bert_layer_weights;
+typedef struct lk_bert_weights {
+  const float* word_emb;                /* embeddings.word_embeddings.weight [vocab x hidden]          */
+  const float* pos_emb;                 /* embeddings.position_embeddings.weight [max_pos x hidden]    */
+  const float* type_emb;                /* embeddings.token_type_embeddings.weight: row 0 is used      */
+  const float *emb_ln_g, *emb_ln_b;     /* embeddings.LayerNorm                                        */
+  const lk_bert_layer_weights* layers;  /* n_layers entries: encoder.layer.<l>                         */
+} lk_bert_weights;
+int lk_bert_create(lk_bert** out, int device, int vocab, int max_pos, int hidden, int heads, int ffn,
+                   int n_layers, float ln_eps, const lk_bert_weights* w);
+/* Operand precision of the linear layers (tcgen05).  LK_F32 (default): split-bf16 operands, three
+ * MMAs per product, fp32-level results.  LK_BF16: operands rounded to bf16, one MMA per product. */
+int lk_bert_set_precision(lk_bert* m, int precision);
+/* input_ids / attention_mask: n_sent x seq_len int32 (mask 0 = padding), host or device (ids_mem);
+ * out: n_sent x hidden fp32, host or device (out_mem); normalize: L2-normalise the pooled rows.
+ * With device outputs the call does not synchronise: lk_bert_check reports a timed-out pipeline. */
+int lk_bert_encode(lk_bert* m, const int32_t* input_ids, const int32_t* attention_mask, int ids_mem,
+                   int64_t n_sent, int seq_len, int normalize, float* out, int out_mem, void* stream);
+int lk_bert_check(lk_bert* m);
+int lk_bert_destroy(lk_bert* m);
+/* One torch.nn.Linear forward through the encoder's tcgen05 path, for tests and bring-up:
+ * y [m x n] = act(x [m x k] w^T + bias) + residual; w [n x k]; bias / residual may be NULL; act 0 =
+ * none, 1 = GELU (erf); precision LK_F32 (split-bf16) or LK_BF16; all pointers fp32 HOST memory;
+ * n % 128 == 0, k % 64 == 0. */
+int lk_linear_forward(int device, const float* x, int64_t m, int k, const float* w, int n,
+                      const float* bias, const float* residual, int act, int precision, float* y);
 
 #ifdef __cplusplus
 }

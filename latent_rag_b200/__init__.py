@@ -12,9 +12,10 @@ from .autoencoders import (ContrastiveAutoencoder, DenoisingAutoencoder, Variati
 from .sharded import ShardedRetriever, shard_bounds
 from .exchange import PeerExchange
 from .evaluation import evaluate_retrieval, rank_positive
+from .sbert import SentenceEncoder
 
 __all__ = [
     "ExactIndex", "merge_topk", "BruteForceRetriever", "EmbeddingCompressor", "FAISSEmbeddingRetriever", "StatsTracker",
     "build_retriever", "ContrastiveAutoencoder", "DenoisingAutoencoder", "VariationalAutoencoder",
-    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval", "rank_positive",
+    "load_autoencoder", "ShardedRetriever", "shard_bounds", "NativeError", "PeerExchange", "evaluate_retrieval", "rank_positive", "SentenceEncoder",
 ]

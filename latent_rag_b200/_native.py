@@ -68,6 +68,13 @@ SYMBOLS = [
     ("lk_comm_collect", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     ("lk_comm_check", c_int, [c_void_p]),
     ("lk_comm_destroy", c_int, [c_void_p]),
+    ("lk_bert_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    ("lk_bert_set_precision", c_int, [c_void_p, c_int]),
+    ("lk_bert_encode", c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
+    ("lk_bert_check", c_int, [c_void_p]),
+    ("lk_bert_destroy", c_int, [c_void_p]),
+    ("lk_linear_forward", c_int, [c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                  c_void_p]),
 ]
 
 

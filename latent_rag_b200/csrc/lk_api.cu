@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "lk_common.cuh"
+#include "lk_host.cuh"
 
 namespace lk {
 void ae_umma_weight_slabs(const float* w, int rows_out, int k_in, int slab_rows, std::vector<unsigned char>* out,
@@ -36,46 +37,6 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 namespace {
 
-// restores the caller's current device (torch tracks it) when an API call returns
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = false;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-struct Buf {
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes) {
-    if (bytes <= cap) return LK_OK;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      want = bytes;
-      e = cudaMalloc(&p, want);
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)", __FILE__, __LINE__);
-    cap = want;
-    return LK_OK;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <typename T> T* as() const { return static_cast<T*>(p); }
-};
-
 TileGeom make_geom(int dim, int storage) {
   TileGeom g;
   g.dim = dim;
@@ -83,24 +44,6 @@ TileGeom make_geom(int dim, int storage) {
   g.dim_pad = round_up(dim, kRowBytes / g.elem_bytes);
   g.kblocks = g.dim_pad * g.elem_bytes / kRowBytes;
   return g;
-}
-
-int check_device(int device, int* sm_count) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
-  if (device < 0 || device >= n) {
-    set_error("device %d out of range (%d visible)", device, n);
-    return LK_ERR_INVALID;
-  }
-  int major = 0;
-  LK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
-  if (major != 10) {
-    set_error("device %d has compute capability %d.x; liblatentknn is built for sm_100a only", device, major);
-    return LK_ERR_UNSUPPORTED;
-  }
-  LK_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
-  return LK_OK;
 }
 
 // row blocks allocated for `rows` rows: whole PAIRS of blocks, because the tcgen05 kernel

@@ -83,3 +83,47 @@ def rank_case(n: int = 200, d: int = 32, seed: int = 17):
     q = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
     noise = torch.from_numpy(rng.standard_normal((n, d)).astype(np.float32))
     return q, q + 1.5 * noise
+
+
+# ---------------------------------------------------------------------------------------
+# sentence encoder: seeded BertModel weights and token batches
+# ---------------------------------------------------------------------------------------
+SBERT_SMALL = dict(vocab=200, max_pos=64, hidden=128, heads=4, ffn=256, layers=2, eps=1e-12)
+
+
+def sbert_weights(cfg: dict, seed: int = 5):
+    """A transformers BertModel state_dict (no pooler) with every tensor random: linear weights
+    N(0, 1/sqrt(fan_in)) so activations keep unit scale through the stack, biases and LayerNorm
+    offsets N(0, 0.1), LayerNorm gains 1 + N(0, 0.1).  torch CPU generator: deterministic on this image."""
+    g = torch.Generator().manual_seed(seed)
+    h, f = cfg["hidden"], cfg["ffn"]
+    rn = lambda *shape, std=1.0: torch.randn(*shape, generator=g) * std  # noqa: E731
+    w = {
+        "embeddings.word_embeddings.weight": rn(cfg["vocab"], h),
+        "embeddings.position_embeddings.weight": rn(cfg["max_pos"], h, std=0.5),
+        "embeddings.token_type_embeddings.weight": rn(2, h, std=0.5),
+        "embeddings.LayerNorm.weight": 1 + rn(h, std=0.1),
+        "embeddings.LayerNorm.bias": rn(h, std=0.1),
+    }
+    for l in range(cfg["layers"]):
+        p = f"encoder.layer.{l}."
+        for name, (o, i) in {"attention.self.query": (h, h), "attention.self.key": (h, h),
+                             "attention.self.value": (h, h), "attention.output.dense": (h, h),
+                             "intermediate.dense": (f, h), "output.dense": (h, f)}.items():
+            w[p + name + ".weight"] = rn(o, i, std=i ** -0.5)
+            w[p + name + ".bias"] = rn(o, std=0.1)
+        for name in ("attention.output.LayerNorm", "output.LayerNorm"):
+            w[p + name + ".weight"] = 1 + rn(h, std=0.1)
+            w[p + name + ".bias"] = rn(h, std=0.1)
+    return w
+
+
+def sbert_tokens(cfg: dict, n_sent: int, seq_len: int, seed: int = 6):
+    """(input_ids int64 [n, s], attention_mask int64 [n, s]): ragged lengths 1..s, one full row."""
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(0, cfg["vocab"], size=(n_sent, seq_len))
+    lens = rng.integers(1, seq_len + 1, size=n_sent)
+    lens[0] = seq_len
+    mask = (np.arange(seq_len)[None, :] < lens[:, None]).astype(np.int64)
+    ids = ids * mask  # padding id 0, like the WordPiece [PAD]
+    return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(mask)

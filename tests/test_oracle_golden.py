@@ -166,3 +166,22 @@ def test_oracle_rank_positive_matches_reference_outputs():
         gold = json.load(f)["ranks"]
     q, d = inputs.rank_case()
     assert oracle.rank_positive(q, d).tolist() == gold
+
+
+# ---------------------------------------------------------------------------------------
+# sentence encoder: the restatement against transformers' own BertModel outputs
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n,s", [("small", 9, 40), ("minilm", 6, 24)])
+def test_sbert_oracle_matches_transformers_outputs(golden, name, n, s):
+    from tests.golden import inputs
+
+    cfg = inputs.SBERT_SMALL if name == "small" else oracle.MINILM_L6
+    g = golden("sbert_golden.npz")
+    w = inputs.sbert_weights(cfg)
+    ids, mask = inputs.sbert_tokens(cfg, n, s)
+    hidden = oracle.bert_hidden_states(w, cfg, ids, mask)
+    np.testing.assert_allclose(hidden[0].numpy(), g[f"{name}_hidden_row0"], atol=2e-5)
+    np.testing.assert_allclose(oracle.sbert_encode(w, cfg, ids, mask, normalize=False).numpy(), g[f"{name}_pooled"], atol=1e-5)
+    emb = oracle.sbert_encode(w, cfg, ids, mask).numpy()
+    np.testing.assert_allclose(emb, g[f"{name}_emb"], atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
