@@ -10,6 +10,9 @@
 //                      the scores and lane = head dimension for the context (head dim == 32)
 //   pool_kernel        masked mean over the tokens (sum / clamp(count, 1e-9)) and L2
 //                      normalisation (x / max(|x|, 1e-12)), one CTA per sentence
+#include <cstdlib>
+#include <cstring>
+
 #include "lk_common.cuh"
 
 namespace lk {
@@ -141,6 +144,146 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const float*
   }
 }
 
+// Register-tiled attention for 64 <= s <= 256 tokens: one CTA per (128 query rows, head, sentence).
+//   phase 1  scores^T[key][query] = K (Q / sqrt(32))^T: every thread owns an 8-query x 16-key tile,
+//            operands transposed in shared memory so that a step over the head dimension is six
+//            128-bit loads for 128 FMAs
+//   phase 2  thread = query row: running max, exp, sum over the keys (masked keys: -inf)
+//   phase 3  context = P V: every thread owns 8 queries x 4 head dimensions; V takes the place of
+//            the Q / K operands, which are dead by then
+// Queries 4g..4g+3 and 64+4g..64+4g+3 belong to thread group g, so the 16 lanes that differ in g
+// read and write consecutive 16-byte pieces of a shared-memory row.
+constexpr int kTileQ = 128;             // query rows per CTA
+constexpr int kQRow = kTileQ + 4;       // row length of the transposed Q operand
+
+__global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __restrict__ qkv,
+                                                              const int32_t* __restrict__ mask, int s, int s_pad,
+                                                              int hidden, float* __restrict__ ctx) {
+  extern __shared__ __align__(16) float attn_smem[];
+  const int k_row = s_pad + 4;
+  float* st = attn_smem;                            // [s_pad][128]  scores^T, then exp(score - max)
+  float* km = st + (size_t)s_pad * kTileQ;          // [s_pad]       0 / -inf per key
+  float* inv = km + s_pad;                          // [128]         1 / sum per query
+  float* qt = inv + kTileQ;                         // [32][132]     Q^T * scale
+  float* kt = qt + kHeadDim * kQRow;                // [32][s_pad+4] K^T
+  float* vs = qt;                                   // [s_pad][32]   V (after phase 1)
+  const int tid = threadIdx.x;
+  const int h = blockIdx.y;
+  const int64_t tok0 = (int64_t)blockIdx.z * s;
+  const int q0 = blockIdx.x * kTileQ;
+  const int ld = 3 * hidden;
+  const float scale = rsqrtf((float)kHeadDim);
+
+  // operands: thread -> (row, 4 head dimensions), 128-byte rows read whole
+  for (int i = tid; i < kTileQ * 8; i += 128) {
+    const int q = i >> 3, d4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + q < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + q0 + q) * ld + h * kHeadDim + d4));
+    qt[(d4 + 0) * kQRow + q] = v.x * scale;
+    qt[(d4 + 1) * kQRow + q] = v.y * scale;
+    qt[(d4 + 2) * kQRow + q] = v.z * scale;
+    qt[(d4 + 3) * kQRow + q] = v.w * scale;
+  }
+  for (int i = tid; i < s_pad * 8; i += 128) {
+    const int j = i >> 3, d4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + hidden + h * kHeadDim + d4));
+    kt[(d4 + 0) * k_row + j] = v.x;
+    kt[(d4 + 1) * k_row + j] = v.y;
+    kt[(d4 + 2) * k_row + j] = v.z;
+    kt[(d4 + 3) * k_row + j] = v.w;
+  }
+  for (int j = tid; j < s_pad; j += 128) km[j] = (j < s && mask[tok0 + j] != 0) ? 0.f : -INFINITY;
+  __syncthreads();
+
+  // phase 1
+  const int n_tiles = 16 * (s_pad >> 4);
+  for (int tile = tid; tile < n_tiles; tile += 128) {
+    const int qg = tile & 15, kg = tile >> 4;
+    float acc[8][16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < kHeadDim; ++d) {
+      const float4 qa = *reinterpret_cast<const float4*>(qt + d * kQRow + 4 * qg);
+      const float4 qb = *reinterpret_cast<const float4*>(qt + d * kQRow + 64 + 4 * qg);
+      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      float kv[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(kt + d * k_row + 16 * kg + 4 * c);
+        kv[4 * c] = t.x; kv[4 * c + 1] = t.y; kv[4 * c + 2] = t.z; kv[4 * c + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(qv[i], kv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float* row = st + (size_t)(16 * kg + j) * kTileQ;
+      *reinterpret_cast<float4*>(row + 4 * qg) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+      *reinterpret_cast<float4*>(row + 64 + 4 * qg) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
+    }
+  }
+  __syncthreads();
+
+  // V over the dead operands (rows past s are zero), then phase 2: thread = query row
+  for (int i = tid; i < s_pad * 8; i += 128) {
+    const int j = i >> 3, d4 = (i & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + 2 * hidden + h * kHeadDim + d4));
+    *reinterpret_cast<float4*>(vs + j * kHeadDim + d4) = v;
+  }
+  {
+    float mx = -INFINITY;
+    for (int j = 0; j < s_pad; ++j) mx = fmaxf(mx, st[(size_t)j * kTileQ + tid] + km[j]);
+    float sum = 0.f;
+    for (int j = 0; j < s_pad; ++j) {
+      const float e = mx > -INFINITY ? expf(st[(size_t)j * kTileQ + tid] + km[j] - mx) : 0.f;
+      st[(size_t)j * kTileQ + tid] = e;
+      sum += e;
+    }
+    inv[tid] = sum > 0.f ? 1.0f / sum : 0.f;
+  }
+  __syncthreads();
+
+  // phase 3
+  {
+    const int qg = tid & 15, dg = tid >> 4;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < s_pad; ++j) {
+      const float4 pa = *reinterpret_cast<const float4*>(st + (size_t)j * kTileQ + 4 * qg);
+      const float4 pb = *reinterpret_cast<const float4*>(st + (size_t)j * kTileQ + 64 + 4 * qg);
+      const float4 vv = *reinterpret_cast<const float4*>(vs + j * kHeadDim + 4 * dg);
+      const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(pv[i], vv.x, acc[i][0]);
+        acc[i][1] = fmaf(pv[i], vv.y, acc[i][1]);
+        acc[i][2] = fmaf(pv[i], vv.z, acc[i][2]);
+        acc[i][3] = fmaf(pv[i], vv.w, acc[i][3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = (i < 4 ? 4 * qg + i : 64 + 4 * qg + i - 4);
+      if (q0 + q < s) {
+        const float r = inv[q];
+        *reinterpret_cast<float4*>(ctx + (tok0 + q0 + q) * hidden + h * kHeadDim + 4 * dg) =
+            make_float4(acc[i][0] * r, acc[i][1] * r, acc[i][2] * r, acc[i][3] * r);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) pool_kernel(const float* __restrict__ x, const int32_t* __restrict__ mask,
                                                    int s, int hidden, int normalize, float* __restrict__ out) {
   __shared__ float red[4];
@@ -208,9 +351,26 @@ int launch_bert_layernorm(float* x, int64_t n_tok, int hidden, const float* g, c
 int launch_bert_attention(const float* qkv, const int32_t* mask, int64_t n_sent, int s, int hidden, int heads,
                           float* ctx, cudaStream_t st) {
   if (n_sent <= 0) return LK_OK;
+  if (n_sent > 65535) {
+    set_error("attention: %lld sentences per call are too many", (long long)n_sent);
+    return LK_ERR_UNSUPPORTED;
+  }
+  const char* force = getenv("LK_ATTN");  // bring-up: "warp" / "tiled"
+  bool tiled = s >= 64 && s <= 256;
+  if (force && s <= 256) tiled = !strcmp(force, "tiled");
+  if (tiled) {
+    const int s_pad = round_up(s, 16);
+    const size_t operands = (size_t)kHeadDim * kQRow + (size_t)kHeadDim * (s_pad + 4), v = (size_t)s_pad * kHeadDim;
+    const size_t smem = ((size_t)s_pad * kTileQ + s_pad + kTileQ + (operands > v ? operands : v)) * sizeof(float);
+    LK_CUDA(cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const dim3 grid((unsigned)((s + kTileQ - 1) / kTileQ), (unsigned)heads, (unsigned)n_sent);
+    attention_tiled_kernel<<<grid, 128, smem, st>>>(qkv, mask, s, s_pad, hidden, ctx);
+    LK_CHECK_LAUNCH("attention_tiled_kernel");
+    return LK_OK;
+  }
   const size_t smem = ((size_t)s * (kHeadDim + 1) + (size_t)s * kHeadDim + (size_t)kAttnWarps * s) * sizeof(float);
-  if (smem > 200 * 1024 || n_sent > 65535) {
-    set_error("attention: %d tokens per sentence / %lld sentences per call are too many", s, (long long)n_sent);
+  if (smem > 200 * 1024) {
+    set_error("attention: %d tokens per sentence are too many", s);
     return LK_ERR_UNSUPPORTED;
   }
   LK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -2,11 +2,11 @@
 embeddings, optionally compressed by an autoencoder, returned as a float32 CPU tensor [N, D].
 
 The autoencoder forward runs on the fused B200 encoder kernel (latent_rag_b200.autoencoders).
-The sentence encoder itself (SBERT all-MiniLM-L6-v2, a third-party transformer with downloaded
-weights) is upstream of the hot path and out of scope: pass any
-object with the sentence-transformers `encode(texts, batch_size=..., convert_to_tensor=True,
-normalize_embeddings=True)` method as `model`, or leave it None to construct
-`SentenceTransformer(base_model_name)` when that package is installed.
+The sentence encoder (SBERT all-MiniLM-L6-v2) is a third-party transformer with downloaded
+weights: pass as `model` any object with the sentence-transformers `encode(texts, batch_size=...,
+convert_to_tensor=True, normalize_embeddings=True)` method -- latent_rag_b200.SentenceEncoder
+runs that forward on the B200 kernels from a BertModel state_dict and a tokenizer -- or leave it
+None to construct `SentenceTransformer(base_model_name)` when that package is installed.
 """
 from __future__ import annotations
 

@@ -114,6 +114,25 @@ def test_encoder_batches_longer_than_one_pass(lrb):
     np.testing.assert_array_equal(host, emb)
 
 
+@pytest.mark.parametrize("s", [64, 100, 128, 200, 256, 300])
+def test_attention_kernels_over_sequence_lengths(lrb, s, monkeypatch):
+    """64..256 tokens take the register-tiled attention kernel, shorter and longer sentences the
+    warp-per-query one; both against the oracle, ragged masks, lengths that are no multiple of 16."""
+    cfg = dict(inputs.SBERT_SMALL, max_pos=320)
+    w = inputs.sbert_weights(cfg)
+    ids, mask = inputs.sbert_tokens(cfg, 7, s, seed=s)
+    enc = lrb.SentenceEncoder(w, heads=cfg["heads"])
+    ref = oracle.sbert_encode(w, cfg, ids, mask).numpy()
+    emb = enc.encode_tokens(ids, mask).cpu().numpy()
+    enc.check()
+    assert np.abs(emb - ref).max() < 1e-4
+    if s <= 256:
+        monkeypatch.setenv("LK_ATTN", "warp")
+        emb_w = enc.encode_tokens(ids, mask).cpu().numpy()
+        assert np.abs(emb_w - ref).max() < 1e-4
+        assert np.abs(emb_w - emb).max() < 2e-5
+
+
 def test_encode_contract_of_the_reference_caller(lrb):
     """EmbeddingCompressor.encode_text (retrieval/embedder.py:24-48) drives the encoder through
     `encode(texts, batch_size=64, convert_to_tensor=True, normalize_embeddings=True)`."""
