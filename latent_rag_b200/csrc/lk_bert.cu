@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "lk_common.cuh"
+#include "lk_planes.cuh"
 
 namespace lk {
 
@@ -30,26 +31,41 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// v[j] = element lane + 32 j of a row of `hidden` values -> normalised in place
+// A lane owns the 8-column chunks lane, lane + 32, ... of a row (hidden % 8 == 0): v[8 c + e] is
+// column 8 (lane + 32 c) + e.  Normalises, writes the fp32 row and -- for the linear layer that
+// reads it next -- the operand planes.
 __device__ __forceinline__ void row_layernorm(float (&v)[kMaxPerLane], int hidden, int lane, const float* g,
-                                              const float* b, float eps, float* out) {
+                                              const float* b, float eps, float* out, unsigned char* planes,
+                                              int64_t row, int n_planes) {
+  const int n_chunks = hidden >> 3;
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j)
-    if (lane + 32 * j < hidden) s += v[j];
+  for (int c = 0; c < kMaxPerLane / 8; ++c)
+    if (lane + 32 * c < n_chunks)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[8 * c + e];
   const float mean = warp_sum(s) / (float)hidden;
   float ss = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j)
-    if (lane + 32 * j < hidden) {
-      const float d = v[j] - mean;
-      ss = fmaf(d, d, ss);
-    }
+  for (int c = 0; c < kMaxPerLane / 8; ++c)
+    if (lane + 32 * c < n_chunks)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[8 * c + e] - mean;
+        ss = fmaf(d, d, ss);
+      }
   const float rstd = 1.0f / sqrtf(warp_sum(ss) / (float)hidden + eps);
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int c = lane + 32 * j;
-    if (c < hidden) out[c] = (v[j] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+  for (int c = 0; c < kMaxPerLane / 8; ++c) {
+    const int col = 8 * (lane + 32 * c);
+    if (lane + 32 * c < n_chunks) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (v[8 * c + e] - mean) * rstd * __ldg(g + col + e) + __ldg(b + col + e);
+      *reinterpret_cast<float4*>(out + col) = make_float4(y[0], y[1], y[2], y[3]);
+      *reinterpret_cast<float4*>(out + col + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      if (planes) store_planes8(planes, hidden >> 6, row, col, y, n_planes);
+    }
   }
 }
 
@@ -57,7 +73,8 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* __restrict
                                                        int vocab, int hidden, const float* __restrict__ word,
                                                        const float* __restrict__ pos, const float* __restrict__ type0,
                                                        const float* __restrict__ g, const float* __restrict__ b,
-                                                       float eps, float* __restrict__ out) {
+                                                       float eps, float* __restrict__ out,
+                                                       unsigned char* __restrict__ planes, int n_planes) {
   const int lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= n_tok) return;
@@ -67,38 +84,48 @@ __global__ void __launch_bounds__(256) embed_ln_kernel(const int32_t* __restrict
   const float* pr = pos + (int64_t)(t % s) * hidden;
   float v[kMaxPerLane];
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int c = lane + 32 * j;
-    v[j] = c < hidden ? __ldg(wr + c) + __ldg(type0 + c) + __ldg(pr + c) : 0.f;
+  for (int c = 0; c < kMaxPerLane / 8; ++c) {
+    const int col = 8 * (lane + 32 * c);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[8 * c + e] = col < hidden ? __ldg(wr + col + e) + __ldg(type0 + col + e) + __ldg(pr + col + e) : 0.f;
   }
-  row_layernorm(v, hidden, lane, g, b, eps, out + t * hidden);
+  row_layernorm(v, hidden, lane, g, b, eps, out + t * hidden, planes, t, n_planes);
 }
 
 __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int64_t n_tok, int hidden,
                                                         const float* __restrict__ g, const float* __restrict__ b,
-                                                        float eps) {
+                                                        float eps, unsigned char* __restrict__ planes, int n_planes) {
   const int lane = threadIdx.x & 31;
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= n_tok) return;
   float* row = x + t * hidden;
   float v[kMaxPerLane];
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int c = lane + 32 * j;
-    v[j] = c < hidden ? row[c] : 0.f;
+  for (int c = 0; c < kMaxPerLane / 8; ++c) {
+    const int col = 8 * (lane + 32 * c);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d = a;
+    if (col < hidden) {
+      a = *reinterpret_cast<const float4*>(row + col);
+      d = *reinterpret_cast<const float4*>(row + col + 4);
+    }
+    v[8 * c] = a.x; v[8 * c + 1] = a.y; v[8 * c + 2] = a.z; v[8 * c + 3] = a.w;
+    v[8 * c + 4] = d.x; v[8 * c + 5] = d.y; v[8 * c + 6] = d.z; v[8 * c + 7] = d.w;
   }
-  row_layernorm(v, hidden, lane, g, b, eps, row);
+  row_layernorm(v, hidden, lane, g, b, eps, row, planes, t, n_planes);
 }
 
 // qkv [n_tok, 3 * hidden] (Q | K | V, head h at columns h * 32), mask [n_tok] (0 = padding key),
-// ctx [n_tok, hidden].  grid (ceil(s / 64), heads, sentences).
+// ctx: the operand planes of the [n_tok, hidden] context (the output projection reads nothing else).
+// grid (ceil(s / 64), heads, sentences).
 __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const float* __restrict__ qkv,
                                                                     const int32_t* __restrict__ mask, int s,
-                                                                    int hidden, float* __restrict__ ctx) {
+                                                                    int hidden, unsigned char* __restrict__ ctx,
+                                                                    int n_planes) {
   extern __shared__ float attn_smem[];
   float* ks = attn_smem;                       // [s][33]
   float* vs = ks + (size_t)s * (kHeadDim + 1);  // [s][32]
   float* ps = vs + (size_t)s * kHeadDim;        // [warps][s]
+  float* cs = ps + (size_t)kAttnWarps * s;      // [warps][32]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
   const int64_t tok0 = (int64_t)blockIdx.z * s;
@@ -139,7 +166,14 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_kernel(const float*
     __syncwarp();
     float acc = 0.f;
     for (int j = 0; j < s; ++j) acc = fmaf(pw[j], vs[j * kHeadDim + lane], acc);
-    ctx[(tok0 + qi) * hidden + h * kHeadDim + lane] = sum > 0.f ? acc / sum : 0.f;
+    cs[warp * kHeadDim + lane] = sum > 0.f ? acc / sum : 0.f;
+    __syncwarp();
+    if (lane < kHeadDim / 8) {  // one 16-byte chunk per plane and lane
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = cs[warp * kHeadDim + 8 * lane + e];
+      store_planes8(ctx, hidden >> 6, tok0 + qi, h * kHeadDim + 8 * lane, y, n_planes);
+    }
     __syncwarp();
   }
 }
@@ -158,7 +192,8 @@ constexpr int kQRow = kTileQ + 4;       // row length of the transposed Q operan
 
 __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __restrict__ qkv,
                                                               const int32_t* __restrict__ mask, int s, int s_pad,
-                                                              int hidden, float* __restrict__ ctx) {
+                                                              int hidden, unsigned char* __restrict__ ctx,
+                                                              int n_planes) {
   extern __shared__ __align__(16) float attn_smem[];
   const int k_row = s_pad + 4;
   float* st = attn_smem;                            // [s_pad][128]  scores^T, then exp(score - max)
@@ -272,13 +307,24 @@ __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __res
         acc[i][3] = fmaf(pv[i], vv.w, acc[i][3]);
       }
     }
+    // lanes l and l ^ 16 hold dimensions 8m..8m+3 and 8m+4..8m+7 of the same queries: after the
+    // exchange both have the 16-byte chunk; each writes it for four of the eight queries
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int q = (i < 4 ? 4 * qg + i : 64 + 4 * qg + i - 4);
-      if (q0 + q < s) {
-        const float r = inv[q];
-        *reinterpret_cast<float4*>(ctx + (tok0 + q0 + q) * hidden + h * kHeadDim + 4 * dg) =
-            make_float4(acc[i][0] * r, acc[i][1] * r, acc[i][2] * r, acc[i][3] * r);
+      const float r = inv[q];
+      float mine[4], other[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mine[e] = acc[i][e] * r;
+        other[e] = __shfl_xor_sync(0xffffffffu, mine[e], 16);
+      }
+      const bool odd = dg & 1;
+      if (q0 + q < s && ((i >> 2) & 1) == (int)odd) {
+        const float y[8] = {odd ? other[0] : mine[0], odd ? other[1] : mine[1], odd ? other[2] : mine[2],
+                            odd ? other[3] : mine[3], odd ? mine[0] : other[0], odd ? mine[1] : other[1],
+                            odd ? mine[2] : other[2], odd ? mine[3] : other[3]};
+        store_planes8(ctx, hidden >> 6, tok0 + q0 + q, h * kHeadDim + 8 * (dg >> 1), y, n_planes);
       }
     }
   }
@@ -332,24 +378,24 @@ int bert_shape_supported(int hidden, int heads, int ffn) {
 
 int launch_bert_embed_ln(const int32_t* ids, int64_t n_tok, int s, int vocab, int hidden, const float* word,
                          const float* pos, const float* type0, const float* g, const float* b, float eps, float* out,
-                         cudaStream_t st) {
+                         unsigned char* planes, int n_planes, cudaStream_t st) {
   if (n_tok <= 0) return LK_OK;
   embed_ln_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(ids, n_tok, s, vocab, hidden, word, pos, type0, g, b,
-                                                               eps, out);
+                                                               eps, out, planes, n_planes);
   LK_CHECK_LAUNCH("embed_ln_kernel");
   return LK_OK;
 }
 
 int launch_bert_layernorm(float* x, int64_t n_tok, int hidden, const float* g, const float* b, float eps,
-                          cudaStream_t st) {
+                          unsigned char* planes, int n_planes, cudaStream_t st) {
   if (n_tok <= 0) return LK_OK;
-  layernorm_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(x, n_tok, hidden, g, b, eps);
+  layernorm_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(x, n_tok, hidden, g, b, eps, planes, n_planes);
   LK_CHECK_LAUNCH("layernorm_kernel");
   return LK_OK;
 }
 
 int launch_bert_attention(const float* qkv, const int32_t* mask, int64_t n_sent, int s, int hidden, int heads,
-                          float* ctx, cudaStream_t st) {
+                          unsigned char* ctx_planes, int n_planes, cudaStream_t st) {
   if (n_sent <= 0) return LK_OK;
   if (n_sent > 65535) {
     set_error("attention: %lld sentences per call are too many", (long long)n_sent);
@@ -364,18 +410,18 @@ int launch_bert_attention(const float* qkv, const int32_t* mask, int64_t n_sent,
     const size_t smem = ((size_t)s_pad * kTileQ + s_pad + kTileQ + (operands > v ? operands : v)) * sizeof(float);
     LK_CUDA(cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const dim3 grid((unsigned)((s + kTileQ - 1) / kTileQ), (unsigned)heads, (unsigned)n_sent);
-    attention_tiled_kernel<<<grid, 128, smem, st>>>(qkv, mask, s, s_pad, hidden, ctx);
+    attention_tiled_kernel<<<grid, 128, smem, st>>>(qkv, mask, s, s_pad, hidden, ctx_planes, n_planes);
     LK_CHECK_LAUNCH("attention_tiled_kernel");
     return LK_OK;
   }
-  const size_t smem = ((size_t)s * (kHeadDim + 1) + (size_t)s * kHeadDim + (size_t)kAttnWarps * s) * sizeof(float);
+  const size_t smem = ((size_t)s * (kHeadDim + 1) + (size_t)s * kHeadDim + (size_t)kAttnWarps * (s + kHeadDim)) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("attention: %d tokens per sentence are too many", s);
     return LK_ERR_UNSUPPORTED;
   }
   LK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const dim3 grid((unsigned)((s + kAttnQueries - 1) / kAttnQueries), (unsigned)heads, (unsigned)n_sent);
-  attention_kernel<<<grid, kAttnWarps * 32, smem, st>>>(qkv, mask, s, hidden, ctx);
+  attention_kernel<<<grid, kAttnWarps * 32, smem, st>>>(qkv, mask, s, hidden, ctx_planes, n_planes);
   LK_CHECK_LAUNCH("attention_kernel");
   return LK_OK;
 }

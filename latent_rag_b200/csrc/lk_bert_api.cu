@@ -37,7 +37,7 @@ struct lk_bert {
   std::vector<BertLayer> layers;
   std::vector<void*> owned;  // every device allocation of the weights
   int* err_flag = nullptr;
-  Buf ids, mask, x, qkv, ctx, tmp, mid, planes, out;
+  Buf ids, mask, x, qkv, tmp, planes_h, planes_f, out;  // planes_*: operand planes of [tokens, hidden] / [tokens, ffn]
 };
 
 namespace {
@@ -80,7 +80,7 @@ int lk_bert_destroy(lk_bert* m) {
   DeviceGuard guard(m->device);
   for (void* p : m->owned) cudaFree(p);
   if (m->err_flag) cudaFree(m->err_flag);
-  Buf* bufs[] = {&m->ids, &m->mask, &m->x, &m->qkv, &m->ctx, &m->tmp, &m->mid, &m->planes, &m->out};
+  Buf* bufs[] = {&m->ids, &m->mask, &m->x, &m->qkv, &m->tmp, &m->planes_h, &m->planes_f, &m->out};
   for (Buf* b : bufs) b->release();
   delete m;
   return LK_OK;
@@ -188,9 +188,9 @@ int lk_bert_encode(lk_bert* m, const int32_t* input_ids, const int32_t* attentio
   const int64_t t_max = per * seq_len, t_pad = round_up64(t_max, kBlockRows);
   int rc;
   if ((rc = m->x.ensure((size_t)t_max * h * 4)) != LK_OK || (rc = m->qkv.ensure((size_t)t_max * 3 * h * 4)) != LK_OK ||
-      (rc = m->ctx.ensure((size_t)t_max * h * 4)) != LK_OK || (rc = m->tmp.ensure((size_t)t_max * h * 4)) != LK_OK ||
-      (rc = m->mid.ensure((size_t)t_max * f * 4)) != LK_OK ||
-      (rc = m->planes.ensure((size_t)t_pad * (f > h ? f : h) * 4)) != LK_OK)  // 2 planes x 2 bytes per element
+      (rc = m->tmp.ensure((size_t)t_max * h * 4)) != LK_OK ||
+      (rc = m->planes_h.ensure((size_t)t_pad * h * 4)) != LK_OK ||  // 2 planes x 2 bytes per element
+      (rc = m->planes_f.ensure((size_t)t_pad * f * 4)) != LK_OK)
     return rc;
   if (ids_mem == LK_HOST)
     if ((rc = m->ids.ensure((size_t)t_max * 4)) != LK_OK || (rc = m->mask.ensure((size_t)t_max * 4)) != LK_OK) return rc;
@@ -198,13 +198,14 @@ int lk_bert_encode(lk_bert* m, const int32_t* input_ids, const int32_t* attentio
     if ((rc = m->out.ensure((size_t)per * h * 4)) != LK_OK) return rc;
   float* x = m->x.as<float>();
   float* tmp = m->tmp.as<float>();
-  unsigned char* planes = m->planes.as<unsigned char>();
-
-  auto linear = [&](const float* in, int k, const unsigned char* w, int n, const float* bias, const float* residual,
-                    int act, float* y, int64_t t) {
-    int r = launch_ae_split_rows(in, t, k, np, planes, st);
-    if (r != LK_OK) return r;
-    return launch_gemm_umma(planes, t, k, w, n, bias, residual, act, np, y, m->err_flag, m->sm_count, st);
+  // Every activation a linear layer reads is written as operand planes by the kernel that produces
+  // it (LayerNorm, attention, the GELU layer's epilogue): ph holds x / the context / the
+  // post-attention state in turn, pf the feed-forward activations.
+  unsigned char* ph = m->planes_h.as<unsigned char>();
+  unsigned char* pf = m->planes_f.as<unsigned char>();
+  auto linear = [&](const unsigned char* in, int k, const unsigned char* w, int n, const float* bias,
+                    const float* residual, int act, float* y, unsigned char* y_planes, int64_t t) {
+    return launch_gemm_umma(in, t, k, w, n, bias, residual, act, np, y, y_planes, m->err_flag, m->sm_count, st);
   };
 
   for (int64_t s0 = 0; s0 < n_sent; s0 += per) {
@@ -217,17 +218,17 @@ int lk_bert_encode(lk_bert* m, const int32_t* input_ids, const int32_t* attentio
       ids = m->ids.as<int32_t>();
       mask = m->mask.as<int32_t>();
     }
-    rc = launch_bert_embed_ln(ids, t, seq_len, m->vocab, h, m->word, m->pos, m->type0, m->emb_g, m->emb_b, m->eps, x, st);
+    rc = launch_bert_embed_ln(ids, t, seq_len, m->vocab, h, m->word, m->pos, m->type0, m->emb_g, m->emb_b, m->eps, x, ph,
+                              np, st);
     if (rc != LK_OK) return rc;
     for (const BertLayer& L : m->layers) {
-      if ((rc = linear(x, h, L.wqkv, 3 * h, L.bqkv, nullptr, 0, m->qkv.as<float>(), t)) != LK_OK) return rc;
-      rc = launch_bert_attention(m->qkv.as<float>(), mask, ns, seq_len, h, m->heads, m->ctx.as<float>(), st);
-      if (rc != LK_OK) return rc;
-      if ((rc = linear(m->ctx.as<float>(), h, L.wo, h, L.bo, x, 0, tmp, t)) != LK_OK) return rc;
-      if ((rc = launch_bert_layernorm(tmp, t, h, L.ln1_g, L.ln1_b, m->eps, st)) != LK_OK) return rc;
-      if ((rc = linear(tmp, h, L.w1, f, L.b1, nullptr, 1, m->mid.as<float>(), t)) != LK_OK) return rc;
-      if ((rc = linear(m->mid.as<float>(), f, L.w2, h, L.b2, tmp, 0, x, t)) != LK_OK) return rc;
-      if ((rc = launch_bert_layernorm(x, t, h, L.ln2_g, L.ln2_b, m->eps, st)) != LK_OK) return rc;
+      if ((rc = linear(ph, h, L.wqkv, 3 * h, L.bqkv, nullptr, 0, m->qkv.as<float>(), nullptr, t)) != LK_OK) return rc;
+      if ((rc = launch_bert_attention(m->qkv.as<float>(), mask, ns, seq_len, h, m->heads, ph, np, st)) != LK_OK) return rc;
+      if ((rc = linear(ph, h, L.wo, h, L.bo, x, 0, tmp, nullptr, t)) != LK_OK) return rc;
+      if ((rc = launch_bert_layernorm(tmp, t, h, L.ln1_g, L.ln1_b, m->eps, ph, np, st)) != LK_OK) return rc;
+      if ((rc = linear(ph, h, L.w1, f, L.b1, nullptr, 1, nullptr, pf, t)) != LK_OK) return rc;
+      if ((rc = linear(pf, f, L.w2, h, L.b2, tmp, 0, x, nullptr, t)) != LK_OK) return rc;
+      if ((rc = launch_bert_layernorm(x, t, h, L.ln2_g, L.ln2_b, m->eps, ph, np, st)) != LK_OK) return rc;
     }
     float* dst = out_mem == LK_HOST ? m->out.as<float>() : out + s0 * h;
     if ((rc = launch_bert_pool(x, mask, ns, seq_len, h, normalize, dst, st)) != LK_OK) return rc;
@@ -289,7 +290,7 @@ int lk_linear_forward(int device, const float* x, int64_t m, int k, const float*
   const int np = precision == LK_BF16 ? 1 : 2;
   if ((rc = launch_ae_split_rows(dx.as<float>(), m, k, np, dp.as<unsigned char>(), nullptr)) != LK_OK) return done(rc);
   rc = launch_gemm_umma(dp.as<unsigned char>(), m, k, dw.as<unsigned char>(), n, bias ? db.as<float>() : nullptr,
-                        residual ? dr.as<float>() : nullptr, act, np, dy.as<float>(), de.as<int>(), sm, nullptr);
+                        residual ? dr.as<float>() : nullptr, act, np, dy.as<float>(), nullptr, de.as<int>(), sm, nullptr);
   if (rc != LK_OK) return done(rc);
   int flag = 0;
   e = cudaMemcpy(y, dy.p, yb, cudaMemcpyDeviceToHost);

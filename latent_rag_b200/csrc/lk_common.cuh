@@ -174,19 +174,22 @@ int launch_ae_umma(const unsigned char* x_slabs, int64_t m, int d_in, int d_hidd
 // linear layer Y = act(X W^T + b) (+ R) on tcgen05 (lk_gemm_umma.cu): X / W as split-bf16 slab planes
 // (launch_ae_split_rows / ae_umma_weight_slabs with 128-row slabs), n % 128 == 0, k % 64 == 0
 int gemm_umma_supported(int n, int k);
+// y: fp32 [m, n], or null with y_planes: the result as operand planes of the next layer
 int launch_gemm_umma(const unsigned char* x_slabs, int64_t m, int k, const unsigned char* w_slabs, int n,
-                     const float* bias, const float* residual, int act, int n_planes, float* y, int* err_flag,
-                     int sm_count, cudaStream_t st);
+                     const float* bias, const float* residual, int act, int n_planes, float* y,
+                     unsigned char* y_planes, int* err_flag, int sm_count, cudaStream_t st);
 
 // sentence-encoder kernels (lk_bert.cu); head dimension 32, hidden <= 1024
 int bert_shape_supported(int hidden, int heads, int ffn);
 int launch_bert_embed_ln(const int32_t* ids, int64_t n_tok, int s, int vocab, int hidden, const float* word,
                          const float* pos, const float* type0, const float* g, const float* b, float eps, float* out,
-                         cudaStream_t st);
+                         unsigned char* planes, int n_planes, cudaStream_t st);
+// LayerNorm in place; planes (optional): the operand planes of the result for the next linear layer
 int launch_bert_layernorm(float* x, int64_t n_tok, int hidden, const float* g, const float* b, float eps,
-                          cudaStream_t st);
+                          unsigned char* planes, int n_planes, cudaStream_t st);
+// the context leaves as operand planes only (the output projection is its one reader)
 int launch_bert_attention(const float* qkv, const int32_t* mask, int64_t n_sent, int s, int hidden, int heads,
-                          float* ctx, cudaStream_t st);
+                          unsigned char* ctx_planes, int n_planes, cudaStream_t st);
 int launch_bert_pool(const float* x, const int32_t* mask, int64_t n_sent, int s, int hidden, int normalize, float* out,
                      cudaStream_t st);
 

@@ -11,9 +11,11 @@
 // load time), so a K step of one 128 x 128 output tile is four 16 KB cp.async.bulk copies into a
 // 64 KB stage and 12 MMAs of 128 x 128 x 16.  Warp 0 produces, warp 1 issues, warps 4-11 read the
 // accumulator (two of them in TMEM: the epilogue of tile t overlaps the MMAs of tile t+1), add the
-// bias, apply GELU / the residual and store fp32 rows.  Persistent CTAs, tiles n-fastest so the X
+// bias, apply GELU / the residual and store fp32 rows -- or, when the only reader is the next linear
+// layer, that layer's operand planes directly.  Persistent CTAs, tiles n-fastest so the X
 // planes of an m tile are re-read from L2.
 #include "lk_common.cuh"
+#include "lk_planes.cuh"
 #include "lk_ptx.cuh"
 
 namespace lk {
@@ -36,7 +38,8 @@ struct GemmParams {
   const unsigned char* w_slabs;
   const float* bias;      // [n] or null
   const float* residual;  // [m, n] or null
-  float* y;               // [m, n]
+  float* y;               // [m, n] fp32, or null:
+  unsigned char* y_planes;  // the result as operand planes (the next linear layer's X)
   int64_t m;
   int n, m_tiles, n_tiles, nkb;
   int act;                // 0 none, 1 GELU (erf)
@@ -202,9 +205,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_umma_kernel(const GemmParams
               v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
             }
           }
-          float4* out = reinterpret_cast<float4*>(p.y + grow * p.n + col);
+          if (p.y) {
+            float4* out = reinterpret_cast<float4*>(p.y + grow * p.n + col);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float y8[8] = {v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3],
+                                   v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]};
+              store_planes8(p.y_planes, p.n >> 6, grow, col + 8 * c, y8, p.np);
+            }
+          }
         }
       }
       ptx::tc_fence_before();
@@ -226,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_umma_kernel(const GemmParams
 int gemm_umma_supported(int n, int k) { return n >= kBlockRows && n % kBlockRows == 0 && k >= 64 && k % 64 == 0; }
 
 int launch_gemm_umma(const unsigned char* x_slabs, int64_t m, int k, const unsigned char* w_slabs, int n,
-                     const float* bias, const float* residual, int act, int n_planes, float* y, int* err_flag,
-                     int sm_count, cudaStream_t st) {
+                     const float* bias, const float* residual, int act, int n_planes, float* y,
+                     unsigned char* y_planes, int* err_flag, int sm_count, cudaStream_t st) {
   if (m <= 0) return LK_OK;
   if (!gemm_umma_supported(n, k)) {
     set_error("tcgen05 linear layer: unsupported shape (n=%d, k=%d)", n, k);
@@ -239,6 +251,7 @@ int launch_gemm_umma(const unsigned char* x_slabs, int64_t m, int k, const unsig
   p.bias = bias;
   p.residual = residual;
   p.y = y;
+  p.y_planes = y_planes;
   p.m = m;
   p.n = n;
   p.m_tiles = (int)((m + kBlockRows - 1) / kBlockRows);
