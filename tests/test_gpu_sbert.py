@@ -169,6 +169,34 @@ def test_encode_contract_of_the_reference_caller(lrb):
         lrb.SentenceEncoder(plain, heads=cfg["heads"]).encode(["no tokenizer"])
 
 
+def test_tokens_to_neighbours_pipeline(lrb):
+    """The reference's whole embedding + retrieval chain on the device (main.py: corpus chunks ->
+    EmbeddingCompressor.encode_text = SBERT forward + autoencoder.encode -> retriever; queries
+    the same way -> retrieve): sentence encoder (MiniLM architecture, seeded weights), the shipped
+    contrastive autoencoder, cosine search over the latents -- against the oracle chain."""
+    import os
+
+    cfg = oracle.MINILM_L6
+    w = inputs.sbert_weights(cfg)
+    ids, mask = inputs.sbert_tokens(cfg, 600, 48, seed=11)
+    enc = lrb.SentenceEncoder(w, heads=cfg["heads"])
+    gold = os.path.join(os.path.dirname(__file__), "golden", "ae_weights_cae.npz")
+    ae = lrb.load_autoencoder("cae", gold, device=0)
+    emb = enc.encode_tokens(ids, mask, normalize_embeddings=True)
+    z = ae.encode(emb)  # [600, 64] unit-norm latents, on the device
+    enc.check()
+    r = lrb.BruteForceRetriever(z, [f"chunk {j}" for j in range(600)], None, metric="cosine", precision="fp32")
+    d, i = r.search(z[:40], 5)
+    np.testing.assert_array_equal(i[:, 0], np.arange(40))
+    emb_ref = oracle.sbert_encode(w, cfg, ids, mask)
+    assert (emb.cpu() - emb_ref).abs().max() < 1e-4
+    z_ref = oracle.ae_encode(emb_ref, oracle.load_encoder_weights(np.load(gold), "cae"), "cae")
+    assert (z.cpu() - z_ref).abs().max() < 2e-4
+    d_ref, i_ref = oracle.bruteforce_search(oracle.bruteforce_build(z_ref), z_ref[:40], 5)
+    ok, why = oracle.topk_equivalent(d_ref, i_ref, d, i, rtol=1e-3)  # inputs differ by the encoders' 1e-4
+    assert ok, why
+
+
 def test_encoder_rejects_what_the_kernels_do_not_implement(lrb):
     cfg = dict(inputs.SBERT_SMALL, heads=2)  # head dimension 64
     with pytest.raises(lrb.NativeError):
