@@ -272,15 +272,24 @@ __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __res
     if (j < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + 2 * hidden + h * kHeadDim + d4));
     *reinterpret_cast<float4*>(vs + j * kHeadDim + d4) = v;
   }
-  {
-    float mx = -INFINITY;
-    for (int j = 0; j < s_pad; ++j) mx = fmaxf(mx, st[(size_t)j * kTileQ + tid] + km[j]);
-    float sum = 0.f;
-    for (int j = 0; j < s_pad; ++j) {
-      const float e = mx > -INFINITY ? expf(st[(size_t)j * kTileQ + tid] + km[j] - mx) : 0.f;
-      st[(size_t)j * kTileQ + tid] = e;
-      sum += e;
-    }
+  {  // four independent chains: the loads of a row's scores are 128 floats apart and latency-bound
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 2
+    for (int j = 0; j < s_pad; j += 4)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m4[u], st[(size_t)(j + u) * kTileQ + tid] + km[j + u]);
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    const float base = mx > -INFINITY ? mx : 0.f;  // every key masked: exp(-inf - 0) = 0, no NaN
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int j = 0; j < s_pad; j += 4)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float e = expf(st[(size_t)(j + u) * kTileQ + tid] + km[j + u] - base);
+        st[(size_t)(j + u) * kTileQ + tid] = e;
+        s4[u] += e;
+      }
+    const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     inv[tid] = sum > 0.f ? 1.0f / sum : 0.f;
   }
   __syncthreads();
