@@ -50,6 +50,10 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     assert lib.lk_index_create(ctypes.byref(h), 0, 10, 16, 2, 1, None) == -1  # mahalanobis without L
     assert lib.lk_index_search(None, None, 0, 0, 1, 5, None, None, 0, 0, 0, None) == -1
     assert lib.lk_merge_topk(0, None, None, 1, 0, 1, 1, None, None, 0, None) == -1
+    assert lib.lk_index_search(None, None, 0, 0, 1, 5000, None, None, 0, 0, 0, None) == -1  # k past LK_MAX_K
+    assert lib.lk_bert_create(ctypes.byref(h), 0, 100, 64, 128, 4, 256, 2, 1e-12, None) == -1  # no weights
+    assert lib.lk_bert_encode(None, None, None, 0, 1, 8, 1, None, 0, None) == -1
+    assert lib.lk_linear_forward(0, None, 4, 64, None, 128, None, None, 0, 0, None) == -1
 
 
 def test_sass_contains_blackwell_instructions():
@@ -67,3 +71,7 @@ def test_sass_contains_blackwell_instructions():
     assert "LDTM" in sass, "no tcgen05.ld in the library"
     assert "UBLKCP" in sass, "no bulk async copy (TMA) in the library"
     assert "sm_100a" in sass or "sm_100" in sass
+    # the sentence encoder's linear layers are tcgen05 kernels too
+    gemm = sass[sass.find("gemm_umma_kernel"):]
+    gemm = gemm[: gemm.find("Function :", 100)] if gemm.find("Function :", 100) > 0 else gemm
+    assert "UTCHMMA" in gemm and "UBLKCP" in gemm and "LDTM" in gemm

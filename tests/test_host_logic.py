@@ -141,9 +141,30 @@ def test_new_entry_points_fail_loudly_without_a_device():
         lrb.PeerExchange(0, 0, 1)
 
 
+@pytest.mark.skipif(not NO_GPU, reason="only meaningful on a box without a GPU")
+def test_sentence_encoder_fails_loudly_without_a_device():
+    from tests.golden import inputs
+
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        lrb.SentenceEncoder(inputs.sbert_weights(inputs.SBERT_SMALL), heads=4)
+
+
+def test_sentence_encoder_state_dict_prefixes():
+    """transformers BertModel keys, bare or as sentence-transformers / BertFor* checkpoints carry them."""
+    from latent_rag_b200.sbert import SentenceEncoder
+
+    sd = {"embeddings.word_embeddings.weight": 1, "encoder.layer.0.output.dense.bias": 2, "pooler.dense.weight": 3}
+    assert SentenceEncoder._strip_prefix(sd) == sd
+    for prefix in ("bert.", "0.auto_model.", "auto_model."):
+        got = SentenceEncoder._strip_prefix({prefix + k: v for k, v in sd.items()} | {"cls.predictions.bias": 0})
+        assert got == sd
+    with pytest.raises(KeyError, match="word_embeddings"):
+        SentenceEncoder._strip_prefix({"encoder.layer.0.output.dense.bias": 2})
+
+
 def test_embedding_compressor_needs_a_base_encoder():
-    """The SBERT forward is out of scope: without sentence-transformers and without `model=` the
-    class says so instead of substituting something else."""
+    """Without sentence-transformers and without `model=` (e.g. a latent_rag_b200.SentenceEncoder)
+    the class says so instead of substituting something else."""
     try:
         import sentence_transformers  # noqa: F401
     except ImportError:
