@@ -197,24 +197,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_umma_kernel(const GemmParams
             v[j] = __uint_as_float(r[j]) + bf[j];
             if (p.act == 1) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
           }
-          if (p.residual) {
-            const float4* rr = reinterpret_cast<const float4*>(p.residual + grow * p.n + col);
+          if (p.residual) {  // 256-bit accesses: a thread's piece of its row is a whole 32-byte sector
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = __ldg(rr + j);
-              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            for (int j = 0; j < 4; ++j) {
+              float t[8];
+              ptx::ldg256(p.residual + grow * p.n + col + 8 * j, t);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[8 * j + e] += t[e];
             }
           }
           if (p.y) {
-            float4* out = reinterpret_cast<float4*>(p.y + grow * p.n + col);
+            float* out = p.y + grow * p.n + col;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const float t[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3],
+                                  v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
+              ptx::stg256(out + 8 * j, t);
+            }
           } else {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float y8[8] = {v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3],
-                                   v[8 * c + 4], v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]};
-              store_planes8(p.y_planes, p.n >> 6, grow, col + 8 * c, y8, p.np);
+            for (int c = 0; c < 2; ++c) {
+              float y16[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) y16[e] = v[16 * c + e];
+              store_planes16(p.y_planes, p.n >> 6, grow, col + 16 * c, y16, p.np);
             }
           }
         }

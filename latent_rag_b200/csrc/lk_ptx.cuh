@@ -66,6 +66,25 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   return true;
 }
 
+// ---- 256-bit global accesses (sm_100: LDG.256 / STG.256): a thread moves a whole 32-byte sector,
+// so row-per-thread epilogues issue half the requests of 128-bit accesses.  32-byte aligned.
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
 // ---- thread-block clusters (CTA pairs for tcgen05 cta_group::2) -----------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
