@@ -42,5 +42,24 @@ for c in comms:
 for c in comms:
     c.collect(10, 16)
     c.check()
+# top-k above 128: slab search, crowded slab (refinement down to single blocks), deep merge
+emb = t(3000, 64)
+emb[256:700] = emb[5] + 0.01 * emb[256:700]
+r = lrb.BruteForceRetriever(emb, [""] * 3000, None, metric="cosine")
+d, i = r.search(emb[5:7], 300)
+assert (i >= 0).all() and (np.diff(d, axis=1) <= 0).all()
+lrb.merge_topk(torch.from_numpy(cd).cuda(), torch.from_numpy(ci).cuda(), 200)
+r.retrieve_batch(emb[:4], top_k=50, candidate_k=150)
+# sentence encoder: both attention kernels, both operand precisions
+sys.path.insert(0, ROOT)
+from tests.golden import inputs  # noqa: E402
+
+cfg = dict(inputs.SBERT_SMALL, max_pos=128)
+enc = lrb.SentenceEncoder(inputs.sbert_weights(cfg), heads=cfg["heads"])
+for s_len in (20, 100):
+    ids, mask = inputs.sbert_tokens(cfg, 5, s_len)
+    enc.set_precision("fp32").encode_tokens(ids, mask)
+    enc.set_precision("bf16").encode_tokens(ids.cuda(), mask.cuda())
+enc.check()
 torch.cuda.synchronize()
 print("sanity ok")
