@@ -209,24 +209,43 @@ __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __res
   const int ld = 3 * hidden;
   const float scale = rsqrtf((float)kHeadDim);
 
-  // operands: thread -> (row, 4 head dimensions), 128-byte rows read whole
-  for (int i = tid; i < kTileQ * 8; i += 128) {
-    const int q = i >> 3, d4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q0 + q < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + q0 + q) * ld + h * kHeadDim + d4));
-    qt[(d4 + 0) * kQRow + q] = v.x * scale;
-    qt[(d4 + 1) * kQRow + q] = v.y * scale;
-    qt[(d4 + 2) * kQRow + q] = v.z * scale;
-    qt[(d4 + 3) * kQRow + q] = v.w * scale;
+  // operands: thread -> (row, 4 head dimensions), 128-byte rows read whole.  All the loads of a
+  // batch are issued before the first transposed store, so their latencies overlap.
+  float4 qv[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int i = tid + 128 * it, q = i >> 3, d4 = (i & 7) * 4;
+    qv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + q < s) qv[it] = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + q0 + q) * ld + h * kHeadDim + d4));
   }
-  for (int i = tid; i < s_pad * 8; i += 128) {
-    const int j = i >> 3, d4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + hidden + h * kHeadDim + d4));
-    kt[(d4 + 0) * k_row + j] = v.x;
-    kt[(d4 + 1) * k_row + j] = v.y;
-    kt[(d4 + 2) * k_row + j] = v.z;
-    kt[(d4 + 3) * k_row + j] = v.w;
+  for (int base = 0; base < s_pad * 8; base += 1024) {
+    float4 kv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + tid + 128 * it, j = i >> 3, d4 = (i & 7) * 4;
+      kv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < s) kv[it] = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + hidden + h * kHeadDim + d4));
+    }
+    if (base == 0) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int i = tid + 128 * it, q = i >> 3, d4 = (i & 7) * 4;
+        qt[(d4 + 0) * kQRow + q] = qv[it].x * scale;
+        qt[(d4 + 1) * kQRow + q] = qv[it].y * scale;
+        qt[(d4 + 2) * kQRow + q] = qv[it].z * scale;
+        qt[(d4 + 3) * kQRow + q] = qv[it].w * scale;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + tid + 128 * it, j = i >> 3, d4 = (i & 7) * 4;
+      if (j < s_pad) {
+        kt[(d4 + 0) * k_row + j] = kv[it].x;
+        kt[(d4 + 1) * k_row + j] = kv[it].y;
+        kt[(d4 + 2) * k_row + j] = kv[it].z;
+        kt[(d4 + 3) * k_row + j] = kv[it].w;
+      }
+    }
   }
   for (int j = tid; j < s_pad; j += 128) km[j] = (j < s && mask[tok0 + j] != 0) ? 0.f : -INFINITY;
   __syncthreads();
@@ -266,11 +285,19 @@ __global__ void __launch_bounds__(128) attention_tiled_kernel(const float* __res
   __syncthreads();
 
   // V over the dead operands (rows past s are zero), then phase 2: thread = query row
-  for (int i = tid; i < s_pad * 8; i += 128) {
-    const int j = i >> 3, d4 = (i & 7) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < s) v = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + 2 * hidden + h * kHeadDim + d4));
-    *reinterpret_cast<float4*>(vs + j * kHeadDim + d4) = v;
+  for (int base = 0; base < s_pad * 8; base += 1024) {
+    float4 vv[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + tid + 128 * it, j = i >> 3, d4 = (i & 7) * 4;
+      vv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < s) vv[it] = __ldg(reinterpret_cast<const float4*>(qkv + (tok0 + j) * ld + 2 * hidden + h * kHeadDim + d4));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + tid + 128 * it, j = i >> 3, d4 = (i & 7) * 4;
+      if (j < s_pad) *reinterpret_cast<float4*>(vs + j * kHeadDim + d4) = vv[it];
+    }
   }
   {  // four independent chains: the loads of a row's scores are 128 floats apart and latency-bound
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
