@@ -37,6 +37,16 @@ def test_python_binding_covers_the_header(lib):
     assert sorted(n for n, _, _ in _native.SYMBOLS) == _declared_symbols()
 
 
+def test_python_constants_match_the_header():
+    from latent_rag_b200 import _native
+
+    with open(os.path.join(ROOT, "include", "latentknn.h")) as f:
+        defines = dict(re.findall(r"#define\s+(LK_[A-Z_]+)\s+(\d+)", f.read()))
+    for name in ("LK_MAX_K", "LK_MAX_K_FUSED", "LK_MAX_WORLD", "LK_IPC_HANDLE_BYTES"):
+        assert int(defines[name]) == getattr(_native, name), name
+    assert _native.load().lk_abi_version() == int(defines["LK_ABI_VERSION"])
+
+
 def test_abi_version_and_error_string(lib):
     assert lib.lk_abi_version() == 1
     assert isinstance(lib.lk_last_error(), bytes)

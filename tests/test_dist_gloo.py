@@ -56,7 +56,8 @@ def _worker(rank, world, port, metric, k, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,metric,k", [(2, "cosine", 10), (2, "euclidean", 5), (3, "cosine", 120)])
+@pytest.mark.parametrize("world,metric,k", [(2, "cosine", 10), (2, "euclidean", 5), (3, "cosine", 120),
+                                            (2, "cosine", 200)])  # 200: more than a shard holds, above one fused pass
 def test_sharded_search_equals_single_shard(tmp_path, world, metric, k):
     import oracle
 
