@@ -5,11 +5,13 @@ The autoencoder forward runs on the fused B200 encoder kernel (latent_rag_b200.a
 The sentence encoder (SBERT all-MiniLM-L6-v2) is a third-party transformer with downloaded
 weights: pass as `model` any object with the sentence-transformers `encode(texts, batch_size=...,
 convert_to_tensor=True, normalize_embeddings=True)` method -- latent_rag_b200.SentenceEncoder
-runs that forward on the B200 kernels from a BertModel state_dict and a tokenizer -- or leave it
-None to construct `SentenceTransformer(base_model_name)` when that package is installed.
+runs that forward on the B200 kernels from a BertModel state_dict and a tokenizer.  With `model`
+None, a `base_model_name` that is a local checkpoint directory is loaded into a SentenceEncoder;
+any other name constructs `SentenceTransformer(base_model_name)` when that package is installed.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -19,6 +21,10 @@ class EmbeddingCompressor:
     def __init__(self, base_model_name: str = "sentence-transformers/all-MiniLM-L6-v2", autoencoder=None,
                  device: Optional[str] = None, *, model=None):
         self.device = device or "cuda"
+        if model is None and os.path.isdir(base_model_name) and os.path.exists(os.path.join(base_model_name, "config.json")):
+            from ..sbert import SentenceEncoder
+
+            model = SentenceEncoder.from_pretrained(base_model_name, device=torch.device(self.device).index)
         if model is None:
             try:
                 from sentence_transformers import SentenceTransformer

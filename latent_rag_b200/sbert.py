@@ -14,6 +14,8 @@ feed token ids to `encode_tokens` directly.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes
+import json
+import os
 from ctypes import POINTER, Structure, byref, c_float, c_void_p
 from typing import Callable, Dict, List, Mapping, Optional, Sequence, Union
 
@@ -124,6 +126,65 @@ class SentenceEncoder:
                                            self.layers, c_float(self.ln_eps), byref(w)), "lk_bert_create")
         del keep
         self.set_precision(precision)
+
+    # -- checkpoint directories ------------------------------------------------------------
+    @staticmethod
+    def read_checkpoint_dir(path: str) -> dict:
+        """What a local sentence-transformers / transformers checkpoint directory says about the model:
+        {"heads", "ln_eps", "max_seq_length", "weights": path} -- and a ValueError for anything the
+        kernels do not implement (a non-GELU activation, relative positions, a pooling other than the mean)."""
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = json.load(f)
+        if cfg.get("hidden_act", "gelu") != "gelu":
+            raise ValueError(f"hidden_act={cfg['hidden_act']!r}: only the erf GELU of BERT is implemented")
+        if cfg.get("position_embedding_type", "absolute") != "absolute":
+            raise ValueError("only absolute position embeddings are implemented")
+        max_seq = int(cfg.get("max_position_embeddings", 512))
+        sb = os.path.join(path, "sentence_bert_config.json")
+        if os.path.exists(sb):
+            with open(sb) as f:
+                max_seq = min(max_seq, int(json.load(f).get("max_seq_length") or max_seq))
+        pool = os.path.join(path, "1_Pooling", "config.json")
+        if os.path.exists(pool):
+            with open(pool) as f:
+                pc = json.load(f)
+            others = [k for k, v in pc.items() if k.startswith("pooling_mode_") and v and k != "pooling_mode_mean_tokens"]
+            if not pc.get("pooling_mode_mean_tokens", True) or others:
+                raise ValueError(f"only mean pooling is implemented (1_Pooling/config.json: {pc})")
+        for name in ("model.safetensors", "pytorch_model.bin"):
+            if os.path.exists(os.path.join(path, name)):
+                weights = os.path.join(path, name)
+                break
+        else:
+            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
+        return {"heads": int(cfg["num_attention_heads"]), "ln_eps": float(cfg.get("layer_norm_eps", 1e-12)),
+                "max_seq_length": max_seq, "weights": weights}
+
+    @classmethod
+    def from_pretrained(cls, path: str, *, device: Optional[int] = None, precision: str = "fp32",
+                        tokenizer: Optional[Callable] = None) -> "SentenceEncoder":
+        """A LOCAL checkpoint directory (config.json + model.safetensors / pytorch_model.bin, as
+        `SentenceTransformer(name)` downloads it; nothing is fetched).  Without `tokenizer` the
+        directory's own one is loaded through transformers and applied with padding to the longest
+        sentence of a call and truncation to the model's max_seq_length."""
+        info = cls.read_checkpoint_dir(path)
+        if info["weights"].endswith(".safetensors"):
+            from safetensors.torch import load_file
+
+            sd = load_file(info["weights"])
+        else:
+            sd = torch.load(info["weights"], map_location="cpu", weights_only=True)
+        if tokenizer is None:
+            from transformers import AutoTokenizer
+
+            tok = AutoTokenizer.from_pretrained(path, local_files_only=True)
+            max_len = info["max_seq_length"]
+
+            def tokenizer(texts):
+                return tok(list(texts), padding=True, truncation=True, max_length=max_len, return_tensors="pt")
+
+        return cls(sd, heads=info["heads"], ln_eps=info["ln_eps"], device=device, tokenizer=tokenizer,
+                   max_seq_length=info["max_seq_length"], precision=precision)
 
     @staticmethod
     def _strip_prefix(state_dict: Mapping[str, object]) -> Dict[str, object]:

@@ -127,3 +127,31 @@ def sbert_tokens(cfg: dict, n_sent: int, seq_len: int, seed: int = 6):
     mask = (np.arange(seq_len)[None, :] < lens[:, None]).astype(np.int64)
     ids = ids * mask  # padding id 0, like the WordPiece [PAD]
     return torch.from_numpy(ids.astype(np.int64)), torch.from_numpy(mask)
+
+
+def write_sbert_checkpoint_dir(path: str, cfg: dict, weights, max_seq_length: int = 16, safetensors: bool = False):
+    """A sentence-transformers style checkpoint directory (what `SentenceTransformer(name)` downloads):
+    BertConfig, weights, a WordPiece vocabulary of cfg["vocab"] entries, the pooling / max-length side files."""
+    import json
+    import os
+
+    os.makedirs(os.path.join(path, "1_Pooling"), exist_ok=True)
+    json.dump({"architectures": ["BertModel"], "model_type": "bert", "vocab_size": cfg["vocab"],
+               "hidden_size": cfg["hidden"], "num_hidden_layers": cfg["layers"], "num_attention_heads": cfg["heads"],
+               "intermediate_size": cfg["ffn"], "max_position_embeddings": cfg["max_pos"], "layer_norm_eps": cfg["eps"],
+               "hidden_act": "gelu", "position_embedding_type": "absolute", "type_vocab_size": 2},
+              open(os.path.join(path, "config.json"), "w"))
+    json.dump({"max_seq_length": max_seq_length, "do_lower_case": False}, open(os.path.join(path, "sentence_bert_config.json"), "w"))
+    json.dump({"word_embedding_dimension": cfg["hidden"], "pooling_mode_cls_token": False, "pooling_mode_mean_tokens": True,
+               "pooling_mode_max_tokens": False}, open(os.path.join(path, "1_Pooling", "config.json"), "w"))
+    words = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "the", "quick", "brown", "fox", "##s", "jump", "over", "lazy", "dog"]
+    words += [f"w{i}" for i in range(cfg["vocab"] - len(words))]
+    open(os.path.join(path, "vocab.txt"), "w").write("\n".join(words) + "\n")
+    json.dump({"tokenizer_class": "BertTokenizer", "do_lower_case": True, "model_max_length": cfg["max_pos"]},
+              open(os.path.join(path, "tokenizer_config.json"), "w"))
+    if safetensors:
+        from safetensors.torch import save_file
+
+        save_file({k: v.contiguous() for k, v in weights.items()}, os.path.join(path, "model.safetensors"))
+    else:
+        torch.save(dict(weights), os.path.join(path, "pytorch_model.bin"))

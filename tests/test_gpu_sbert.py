@@ -169,6 +169,31 @@ def test_encode_contract_of_the_reference_caller(lrb):
         lrb.SentenceEncoder(plain, heads=cfg["heads"]).encode(["no tokenizer"])
 
 
+@pytest.mark.parametrize("safetensors", [False, True])
+def test_from_pretrained_directory(lrb, tmp_path, safetensors):
+    """A local sentence-transformers checkpoint directory (config, weights, WordPiece vocabulary) loads into
+    the encoder with its own tokenizer; EmbeddingCompressor takes the directory as `base_model_name`, where the
+    reference passes the model name to SentenceTransformer (retrieval/embedder.py:17-18)."""
+    from transformers import AutoTokenizer
+
+    cfg = inputs.SBERT_SMALL
+    w = inputs.sbert_weights(cfg)
+    d = str(tmp_path / "ckpt")
+    inputs.write_sbert_checkpoint_dir(d, cfg, w, max_seq_length=16, safetensors=safetensors)
+    enc = lrb.SentenceEncoder.from_pretrained(d)
+    assert (enc.heads, enc.max_seq_length, enc.layers, enc.vocab) == (cfg["heads"], 16, cfg["layers"], cfg["vocab"])
+    texts = ["the quick brown foxs jump over the lazy dog", "dog", "w7 w8 w9 unknownword the", "lazy " * 40]
+    out = enc.encode(texts, batch_size=64, convert_to_tensor=True, normalize_embeddings=True)
+    tok = AutoTokenizer.from_pretrained(d, local_files_only=True)
+    for r, t in enumerate(texts):
+        one = tok([t], padding=True, truncation=True, max_length=16, return_tensors="pt")
+        ref = oracle.sbert_encode(w, cfg, one["input_ids"], one["attention_mask"]).numpy()
+        assert np.abs(out[r].cpu().numpy() - ref[0]).max() < 1e-4
+    comp = lrb.EmbeddingCompressor(base_model_name=d, device="cuda")
+    z = comp.encode_text(texts, compress=False)
+    np.testing.assert_allclose(z.numpy(), out.cpu().numpy(), atol=1e-6)
+
+
 def test_tokens_to_neighbours_pipeline(lrb):
     """The reference's whole embedding + retrieval chain on the device (main.py: corpus chunks ->
     EmbeddingCompressor.encode_text = SBERT forward + autoencoder.encode -> retriever; queries

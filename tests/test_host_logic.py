@@ -1,5 +1,7 @@
 """Host-side logic that needs no GPU: stats, error conventions, fingerprints, and the rule
 that the product fails loudly (never falls back) without a device."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -160,6 +162,39 @@ def test_sentence_encoder_state_dict_prefixes():
         assert got == sd
     with pytest.raises(KeyError, match="word_embeddings"):
         SentenceEncoder._strip_prefix({"encoder.layer.0.output.dense.bias": 2})
+
+
+def test_sentence_encoder_reads_checkpoint_directories(tmp_path):
+    """config.json / sentence_bert_config.json / 1_Pooling/config.json of a sentence-transformers
+    directory: what is read, and what is refused because the kernels do not implement it."""
+    import json
+
+    from latent_rag_b200.sbert import SentenceEncoder
+    from tests.golden import inputs
+
+    cfg = inputs.SBERT_SMALL
+    d = str(tmp_path / "ckpt")
+    inputs.write_sbert_checkpoint_dir(d, cfg, {"embeddings.word_embeddings.weight": torch.zeros(2, 2)}, max_seq_length=16)
+    info = SentenceEncoder.read_checkpoint_dir(d)
+    assert (info["heads"], info["ln_eps"], info["max_seq_length"]) == (cfg["heads"], cfg["eps"], 16)
+    assert info["weights"].endswith("pytorch_model.bin")
+    from transformers import AutoTokenizer
+
+    tok = AutoTokenizer.from_pretrained(d, local_files_only=True)
+    out = tok(["the quick brown foxs jump", "dog"], padding=True, truncation=True, max_length=6, return_tensors="pt")
+    assert out["input_ids"].shape == (2, 6) and out["attention_mask"][1].tolist() == [1, 1, 1, 0, 0, 0]
+    edit = lambda name, **kw: json.dump({**json.load(open(os.path.join(d, name))), **kw}, open(os.path.join(d, name), "w"))  # noqa: E731
+    edit("config.json", hidden_act="relu")
+    with pytest.raises(ValueError, match="GELU"):
+        SentenceEncoder.read_checkpoint_dir(d)
+    edit("config.json", hidden_act="gelu")
+    edit(os.path.join("1_Pooling", "config.json"), pooling_mode_cls_token=True, pooling_mode_mean_tokens=False)
+    with pytest.raises(ValueError, match="mean pooling"):
+        SentenceEncoder.read_checkpoint_dir(d)
+    edit(os.path.join("1_Pooling", "config.json"), pooling_mode_cls_token=False, pooling_mode_mean_tokens=True)
+    os.remove(os.path.join(d, "pytorch_model.bin"))
+    with pytest.raises(FileNotFoundError):
+        SentenceEncoder.read_checkpoint_dir(d)
 
 
 def test_embedding_compressor_needs_a_base_encoder():
