@@ -1,25 +1,28 @@
 """build_retriever: the switch the reference's pipeline flips (retrieval/retriever.py:17-34,
-called at main.py:248).  Same cfg keys: backend, index_path, index_type, use_gpu."""
+called at main.py:248).  Same cfg keys and defaults -- backend ("faiss"), index_path (None),
+index_type ("hnsw"), use_gpu (False) -- plus the optional `metric` / `precision` of this engine."""
 from __future__ import annotations
 
-from typing import Sequence
+from typing import Any, Dict, Mapping, Sequence
 
 import torch
 
 from .bruteforce import BruteForceRetriever
 from .FAISSEmbeddingRetriever import FAISSEmbeddingRetriever
 
+# cfg key -> (constructor keyword, default) of the FAISS mirror
+_FAISS_KEYS = {"index_path": ("index_path", None), "index_type": ("index_type", "hnsw"), "use_gpu": ("use_gpu", False)}
+
+
+def _picked(cfg: Mapping[str, Any], names: Sequence[str]) -> Dict[str, Any]:
+    return {name: cfg[name] for name in names if name in cfg}
+
 
 def build_retriever(embeddings: torch.Tensor, texts: Sequence[str], doc_ids: Sequence[int], cfg: dict):
-    if cfg.get("backend", "faiss") == "faiss":
-        ret = FAISSEmbeddingRetriever(
-            embedding_dim=embeddings.size(1),
-            index_path=cfg.get("index_path"),
-            index_type=cfg.get("index_type", "hnsw"),
-            use_gpu=cfg.get("use_gpu", False),
-            **({"precision": cfg["precision"]} if "precision" in cfg else {}),
-        )
-        ret.build(embeddings, texts, doc_ids, train=True)
-        return ret
-    extra = {key: cfg[key] for key in ("metric", "precision") if key in cfg}
-    return BruteForceRetriever(embeddings, texts, doc_ids, **extra)
+    backend = cfg.get("backend", "faiss")
+    if backend != "faiss":  # the reference sends every other value to the brute-force class
+        return BruteForceRetriever(embeddings, texts, doc_ids, **_picked(cfg, ("metric", "precision")))
+    kwargs = {kw: cfg.get(key, default) for key, (kw, default) in _FAISS_KEYS.items()}
+    retriever = FAISSEmbeddingRetriever(embeddings.size(1), **kwargs, **_picked(cfg, ("precision",)))
+    retriever.build(embeddings, texts, doc_ids, train=True)
+    return retriever

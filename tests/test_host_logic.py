@@ -207,6 +207,35 @@ def test_embedding_compressor_needs_a_base_encoder():
             lrb.EmbeddingCompressor()
 
 
+def test_build_retriever_reads_the_reference_cfg_keys(monkeypatch):
+    """retrieval/retriever.py:17-34: backend defaults to faiss (index_path None, index_type hnsw,
+    use_gpu False, build(train=True)); any other backend builds the brute-force class."""
+    import latent_rag_b200.retrieval.retriever as mod
+
+    calls = []
+
+    class Rec:
+        def __init__(self, *a, **k):
+            calls.append((type(self).__name__, a[0] if not torch.is_tensor(a[0]) else "emb", k))
+
+        def build(self, *a, **k):
+            calls.append(("build", len(a), k))
+
+    monkeypatch.setattr(mod, "FAISSEmbeddingRetriever", type("FA", (Rec,), {}))
+    monkeypatch.setattr(mod, "BruteForceRetriever", type("BR", (Rec,), {}))
+    emb = torch.zeros(3, 8)
+    mod.build_retriever(emb, ["a"] * 3, [1, 2, 3], {})
+    mod.build_retriever(emb, ["a"] * 3, [1, 2, 3], {"backend": "faiss", "index_type": "flatip", "index_path": "/x",
+                                                     "use_gpu": True, "precision": "fp32"})
+    mod.build_retriever(emb, ["a"] * 3, [1, 2, 3], {"backend": "bruteforce", "metric": "euclidean"})
+    assert calls == [
+        ("FA", 8, {"index_path": None, "index_type": "hnsw", "use_gpu": False}), ("build", 3, {"train": True}),
+        ("FA", 8, {"index_path": "/x", "index_type": "flatip", "use_gpu": True, "precision": "fp32"}),
+        ("build", 3, {"train": True}),
+        ("BR", "emb", {"metric": "euclidean"}),
+    ]
+
+
 def test_sharded_retriever_rejects_unknown_exchange():
     import oracle
 
