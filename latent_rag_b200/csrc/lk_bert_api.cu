@@ -184,6 +184,7 @@ int lk_bert_encode(lk_bert* m, const int32_t* input_ids, const int32_t* attentio
   const int h = m->hidden, f = m->ffn, np = m->precision == LK_BF16 ? 1 : 2;
   int64_t per = kChunkTokens / seq_len;  // sentences per pass
   if (per < 1) per = 1;
+  if (per > 65535) per = 65535;  // sentences are a grid dimension of the attention kernels
   if (per > n_sent) per = n_sent;
   const int64_t t_max = per * seq_len, t_pad = round_up64(t_max, kBlockRows);
   int rc;
