@@ -62,6 +62,14 @@ def _f32(t) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(t, dtype=np.float32))
 
 
+def length_sorted_chunks(texts: Sequence[str], step: int) -> List[List[int]]:
+    """Indices of `texts`, longest first (stable), in runs of `step`: every run is tokenised and padded
+    on its own, so a run's padding is bounded by its own longest sentence (sentence-transformers
+    sorts the same way inside `encode`)."""
+    order = sorted(range(len(texts)), key=lambda i: -len(texts[i]))
+    return [order[lo: lo + step] for lo in range(0, len(order), step)]
+
+
 class SentenceEncoder:
     """state_dict: the tensors of a transformers BertModel (keys may carry a `bert.` or `0.auto_model.`
     prefix, as sentence-transformers checkpoints do); the architecture is read from their shapes.
@@ -253,10 +261,7 @@ class SentenceEncoder:
         single = isinstance(sentences, str)
         texts = [sentences] if single else list(sentences)
         out = torch.empty((len(texts), self.hidden), dtype=torch.float32, device=f"cuda:{self.device}")
-        order = sorted(range(len(texts)), key=lambda i: -len(texts[i]))
-        step = max(int(batch_size), 1) * 16
-        for lo in range(0, len(order), step):
-            pick = order[lo: lo + step]
+        for pick in length_sorted_chunks(texts, max(int(batch_size), 1) * 16):
             tok = self.tokenizer([texts[i] for i in pick])
             ids = torch.as_tensor(tok["input_ids"])[:, : self.max_seq_length]
             mask = torch.as_tensor(tok["attention_mask"])[:, : self.max_seq_length]

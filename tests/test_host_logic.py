@@ -164,6 +164,16 @@ def test_sentence_encoder_state_dict_prefixes():
         SentenceEncoder._strip_prefix({"encoder.layer.0.output.dense.bias": 2})
 
 
+def test_sentence_batches_are_length_sorted():
+    from latent_rag_b200.sbert import length_sorted_chunks
+
+    texts = ["bb", "a", "dddd", "ccc", "", "eeeee", "ff"]
+    chunks = length_sorted_chunks(texts, 3)
+    assert chunks == [[5, 2, 3], [0, 6, 1], [4]]  # longest first, ties in input order
+    assert sorted(i for c in chunks for i in c) == list(range(len(texts)))
+    assert length_sorted_chunks([], 4) == []
+
+
 def test_sentence_encoder_reads_checkpoint_directories(tmp_path):
     """config.json / sentence_bert_config.json / 1_Pooling/config.json of a sentence-transformers
     directory: what is read, and what is refused because the kernels do not implement it."""
