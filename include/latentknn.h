@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LK_ABI_VERSION 1
+#define LK_ABI_VERSION 2
 
 typedef enum lk_status {
   LK_OK = 0,
@@ -83,8 +83,10 @@ int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, 
 int lk_index_add(lk_index* ix, const void* rows, int dtype, int mem, int64_t n_rows, void* stream);
 int lk_index_size(const lk_index* ix, int64_t* out_rows, int* out_dim);
 /* grow the capacity (device-to-device copy of the tiles); FAISSEmbeddingRetriever.build
- * appends to an existing index on every call (FAISSEmbeddingRetriever.py:252-257,294-296) */
-int lk_index_reserve(lk_index* ix, int64_t capacity_rows);
+ * appends to an existing index on every call (FAISSEmbeddingRetriever.py:252-257,294-296).
+ * The copy is ordered on `stream` -- pass the stream the earlier lk_index_add calls ran on (or
+ * synchronise first) -- and the call returns after it has completed. */
+int lk_index_reserve(lk_index* ix, int64_t capacity_rows, void* stream);
 int lk_index_destroy(lk_index* ix);
 
 /* ---- persistence: replaces faiss.write_index / read_index
@@ -92,9 +94,13 @@ int lk_index_destroy(lk_index* ix);
  *      tiled image (not the upstream .faiss format): `tile_bytes` of operand tiles and
  *      `side_bytes` of fp32 side values covering the rows added so far. */
 int lk_index_storage_bytes(const lk_index* ix, int64_t* out_tile_bytes, int64_t* out_side_bytes);
-int lk_index_export(lk_index* ix, void* tiles_host, void* side_host);
-/* fill an empty index created with the same dim / metric / storage */
-int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host, int64_t n_rows);
+/* both copies are ordered on `stream` (behind the adds issued on it) and complete before return */
+int lk_index_export(lk_index* ix, void* tiles_host, void* side_host, void* stream);
+/* fill an empty index created with the same dim / metric / storage.  tile_bytes / side_bytes are
+ * the lengths of the two host buffers and must be exactly what n_rows rows of this geometry take
+ * (lk_index_storage_bytes of the exporting index): a truncated image is LK_ERR_INVALID, never read. */
+int lk_index_import(lk_index* ix, const void* tiles_host, int64_t tile_bytes, const void* side_host,
+                    int64_t side_bytes, int64_t n_rows, void* stream);
 
 /* ---- search: replaces BruteForceRetriever.search (retrieval/bruteforce.py:58-83) and
  *      FAISSEmbeddingRetriever.search (FAISSEmbeddingRetriever.py:314-326).
@@ -146,7 +152,8 @@ int lk_maxsim_rerank(int device, const float* cand_scores, const int64_t* cand_i
  *      retrieved: n_queries x n_retrieved ids (< 0 = padding of a shorter list); the relevant ids of
  *      query q are rel_ids[rel_offsets[q] .. rel_offsets[q+1]); metric m is metric_kind[m]
  *      (0 recall, 1 mrr, 2 ndcg) at cut-off metric_k[m] (<= 0: the whole list); discounts[i] =
- *      1 / log2(i + 2) in float64; out: n_queries x n_metrics float64.  All pointers are device
+ *      1 / log2(i + 2) in float64, max(n_retrieved, largest metric_k) entries (the ideal DCG keeps the
+ *      caller's cut-off when fewer ids were retrieved, retrieval_metrics.py:29); out: n_queries x n_metrics float64.  All pointers are device
  *      memory.  The values equal the reference's bit for bit (same float64 sums, left to right). */
 int lk_retrieval_metrics(int device, const int64_t* retrieved, int64_t n_queries, int n_retrieved,
                          const int64_t* rel_offsets, const int64_t* rel_ids, const int* metric_kind,
@@ -166,7 +173,10 @@ int lk_rank_positive(int device, const float* queries, const float* docs, int64_
  *      host-side process group).  lk_comm_exchange_merge is ONE kernel per rank and call:
  *      it stores this rank's b x k candidates (global ids) straight into every peer's buffer
  *      over NVLink, releases per-query flags, waits for the peers' flags and merges the
- *      world x k candidates of each query.  All ranks must call it in the same order.
+ *      world x k candidates of each query.  All ranks must call it in the same order.  The wait for
+ *      a peer is bounded (60 s; LK_XCHG_TIMEOUT_S overrides) only to turn a dead peer into an error:
+ *      on a timeout the affected queries come back as id -1 / score -inf and lk_comm_check reports
+ *      LK_ERR_CUDA -- callers that keep the outputs on the device must call lk_comm_check.
  *
  *      lk_comm_attach_local / lk_comm_begin / lk_comm_publish / lk_comm_collect split the
  *      same protocol into steps so that several ranks can be driven from ONE process (tests

@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_void_
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "liblatentknn.so")
 
+LK_ABI_VERSION = 2
 LK_F32, LK_BF16 = 0, 1
 LK_HOST, LK_DEVICE = 0, 1
 LK_COSINE, LK_EUCLIDEAN, LK_MAHALANOBIS = 0, 1, 2
@@ -34,7 +35,7 @@ SYMBOLS = [
     ("lk_launch_count", c_int64, []),
     ("lk_index_create", c_int, [POINTER(c_void_p), c_int, c_int64, c_int, c_int, c_int, POINTER(c_double)]),
     ("lk_index_add", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
-    ("lk_index_reserve", c_int, [c_void_p, c_int64]),
+    ("lk_index_reserve", c_int, [c_void_p, c_int64, c_void_p]),
     ("lk_index_size", c_int, [c_void_p, POINTER(c_int64), POINTER(c_int)]),
     ("lk_index_destroy", c_int, [c_void_p]),
     ("lk_index_search", c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_void_p, c_int,
@@ -43,8 +44,8 @@ SYMBOLS = [
     ("lk_index_last_timing", c_int, [c_void_p, POINTER(c_float), POINTER(c_float)]),
     ("lk_index_set_timing", c_int, [c_void_p, c_int]),
     ("lk_index_storage_bytes", c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
-    ("lk_index_export", c_int, [c_void_p, c_void_p, c_void_p]),
-    ("lk_index_import", c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    ("lk_index_export", c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("lk_index_import", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     ("lk_merge_topk", c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                               c_void_p]),
     ("lk_ae_create", c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -100,8 +101,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.lk_abi_version() != 1:
-        raise NativeError(f"liblatentknn ABI {lib.lk_abi_version()} != 1 expected by this package")
+    if lib.lk_abi_version() != LK_ABI_VERSION:
+        raise NativeError(f"liblatentknn ABI {lib.lk_abi_version()} != {LK_ABI_VERSION} expected by this package")
     _lib = lib
     return lib
 

@@ -253,13 +253,17 @@ int lk_index_add(lk_index* ix, const void* rows, int dtype, int mem, int64_t n_r
   return LK_OK;
 }
 
-int lk_index_reserve(lk_index* ix, int64_t capacity_rows) {
+int lk_index_reserve(lk_index* ix, int64_t capacity_rows, void* stream) {
   if (!ix || capacity_rows > 0x7fffff00LL) {
     set_error("lk_index_reserve: bad argument");
     return LK_ERR_INVALID;
   }
   if (capacity_rows <= ix->capacity) return LK_OK;
   DeviceGuard guard(ix->device);
+  // The copies run on the caller's stream, behind the tiling kernels of earlier lk_index_add calls
+  // on it (torch's side streams do not synchronise with the legacy default stream, so a plain
+  // cudaMemcpy could overtake them); the stream is drained before the old buffers are freed.
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t old_blk = alloc_blocks(ix->capacity);
   const int64_t new_blk = alloc_blocks(capacity_rows);
   const size_t bb = (size_t)ix->g.block_bytes();
@@ -267,12 +271,14 @@ int lk_index_reserve(lk_index* ix, int64_t capacity_rows) {
   float* side = nullptr;
   cudaError_t e = cudaMalloc((void**)&tiles, (size_t)new_blk * bb);
   if (e == cudaSuccess) e = cudaMalloc((void**)&side, (size_t)new_blk * kBlockRows * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemcpy(tiles, ix->tiles, (size_t)old_blk * bb, cudaMemcpyDeviceToDevice);
-  if (e == cudaSuccess) e = cudaMemset(tiles + (size_t)old_blk * bb, 0, (size_t)(new_blk - old_blk) * bb);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tiles, ix->tiles, (size_t)old_blk * bb, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(tiles + (size_t)old_blk * bb, 0, (size_t)(new_blk - old_blk) * bb, st);
   if (e == cudaSuccess)
-    e = cudaMemcpy(side, ix->side, (size_t)old_blk * kBlockRows * sizeof(float), cudaMemcpyDeviceToDevice);
+    e = cudaMemcpyAsync(side, ix->side, (size_t)old_blk * kBlockRows * sizeof(float), cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess)
-    e = cudaMemset(side + (size_t)old_blk * kBlockRows, 0xFF, (size_t)(new_blk - old_blk) * kBlockRows * sizeof(float));
+    e = cudaMemsetAsync(side + (size_t)old_blk * kBlockRows, 0xFF,
+                        (size_t)(new_blk - old_blk) * kBlockRows * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     if (tiles) cudaFree(tiles);
     if (side) cudaFree(side);
@@ -294,17 +300,20 @@ int lk_index_storage_bytes(const lk_index* ix, int64_t* out_tile_bytes, int64_t*
   return LK_OK;
 }
 
-int lk_index_export(lk_index* ix, void* tiles_host, void* side_host) {
+int lk_index_export(lk_index* ix, void* tiles_host, void* side_host, void* stream) {
   if (!ix || !tiles_host || !side_host) return LK_ERR_INVALID;
   DeviceGuard guard(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);  // behind the adds issued on this stream
   int64_t tb = 0, sb = 0;
   lk_index_storage_bytes(ix, &tb, &sb);
-  LK_CUDA(cudaMemcpy(tiles_host, ix->tiles, (size_t)tb, cudaMemcpyDeviceToHost));
-  LK_CUDA(cudaMemcpy(side_host, ix->side, (size_t)sb, cudaMemcpyDeviceToHost));
+  LK_CUDA(cudaMemcpyAsync(tiles_host, ix->tiles, (size_t)tb, cudaMemcpyDeviceToHost, st));
+  LK_CUDA(cudaMemcpyAsync(side_host, ix->side, (size_t)sb, cudaMemcpyDeviceToHost, st));
+  LK_CUDA(cudaStreamSynchronize(st));
   return LK_OK;
 }
 
-int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host, int64_t n_rows) {
+int lk_index_import(lk_index* ix, const void* tiles_host, int64_t tile_bytes, const void* side_host,
+                    int64_t side_bytes, int64_t n_rows, void* stream) {
   if (!ix || !tiles_host || !side_host || n_rows < 0) return LK_ERR_INVALID;
   if (ix->n_rows != 0) {
     set_error("lk_index_import: the index is not empty");
@@ -314,10 +323,19 @@ int lk_index_import(lk_index* ix, const void* tiles_host, const void* side_host,
     set_error("lk_index_import: %lld rows exceed the capacity %lld", (long long)n_rows, (long long)ix->capacity);
     return LK_ERR_CAPACITY;
   }
-  DeviceGuard guard(ix->device);
   const int64_t nblk = (n_rows + kBlockRows - 1) / kBlockRows;
-  LK_CUDA(cudaMemcpy(ix->tiles, tiles_host, (size_t)(nblk * ix->g.block_bytes()), cudaMemcpyHostToDevice));
-  LK_CUDA(cudaMemcpy(ix->side, side_host, (size_t)nblk * kBlockRows * sizeof(float), cudaMemcpyHostToDevice));
+  const int64_t want_tiles = nblk * ix->g.block_bytes(), want_side = nblk * kBlockRows * (int64_t)sizeof(float);
+  if (tile_bytes != want_tiles || side_bytes != want_side) {  // a truncated or foreign image must not be read past its end
+    set_error("lk_index_import: %lld rows of dim %d need %lld tile bytes and %lld side bytes, got %lld and %lld",
+              (long long)n_rows, ix->dim, (long long)want_tiles, (long long)want_side, (long long)tile_bytes,
+              (long long)side_bytes);
+    return LK_ERR_INVALID;
+  }
+  DeviceGuard guard(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LK_CUDA(cudaMemcpyAsync(ix->tiles, tiles_host, (size_t)want_tiles, cudaMemcpyHostToDevice, st));
+  LK_CUDA(cudaMemcpyAsync(ix->side, side_host, (size_t)want_side, cudaMemcpyHostToDevice, st));
+  LK_CUDA(cudaStreamSynchronize(st));  // the caller may free the host buffers on return
   ix->n_rows = n_rows;
   return LK_OK;
 }

@@ -19,6 +19,7 @@
 // Against an all-gather this removes two collectives, their launch gaps and the staging
 // copies from the batch-1 critical path; the payload is tiny (world * k * 12 bytes per
 // query), so the exchange is latency- not bandwidth-bound.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -29,7 +30,11 @@ namespace lk {
 namespace {
 
 constexpr int kXThreads = 256;
-constexpr long long kSpinCycles = 4000LL * 1000 * 1000;  // ~2 s
+// A rank may legitimately arrive late (a cudaMalloc in lk_index_reserve, a first-call
+// cudaFuncSetAttribute, a crowded shard, a host-side pause): the wait for a peer's flag is bounded
+// only to turn a dead peer into an error instead of a hang.  LK_XCHG_TIMEOUT_S overrides the default.
+constexpr double kDefaultTimeoutS = 60.0;
+constexpr double kSpinClockHz = 2.0e9;
 
 struct XView {  // one rank's symmetric buffer
   float* scores;     // [2][world][max_b][max_k]
@@ -51,6 +56,7 @@ struct XParams {
   int64_t* out_i;
   int* err_flag;
   int phases;                // bit 0: publish, bit 1: wait + merge
+  long long spin_cycles;     // bound of the wait for one peer flag
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
@@ -93,15 +99,20 @@ __global__ void __launch_bounds__(kXThreads) exchange_merge_kernel(const XParams
       const unsigned* f = me.flag + (int64_t)slot * slot_rows + (int64_t)tid * p.max_b + q;
       const long long t0 = clock64();
       while (ld_acquire_sys(f) != p.epoch) {
-        if (clock64() - t0 > kSpinCycles) {
+        if (clock64() - t0 > p.spin_cycles) {
           s_timeout = 1;
           break;
         }
       }
     }
     __syncthreads();
-    if (s_timeout) {
+    if (s_timeout) {  // a peer never published: this and the remaining queries come back empty, never uninitialised
       if (tid == 0) atomicCAS(p.err_flag, 0, 301);
+      for (int64_t qq = q; qq < p.b; qq += gridDim.x)
+        for (int j = tid; j < p.k; j += kXThreads) {
+          p.out_s[qq * p.k + j] = -INFINITY;
+          p.out_i[qq * p.k + j] = -1;
+        }
       return;
     }
     if (warp == 0) {  // world * k candidates (<= 16 * 128), one warp
@@ -190,6 +201,12 @@ int run_exchange(lk_comm* c, const float* local_s, const int64_t* local_i, int64
   p.out_i = out_i;
   p.err_flag = c->err_flag;
   p.phases = phases;
+  double timeout_s = kDefaultTimeoutS;
+  if (const char* e = getenv("LK_XCHG_TIMEOUT_S")) {
+    const double v = atof(e);
+    if (v > 0.0) timeout_s = v;
+  }
+  p.spin_cycles = (long long)(timeout_s * kSpinClockHz);
   const int64_t resident = (int64_t)c->sm_count * 4;  // 256 threads, ~3 KB smem: at least 4 CTAs per SM fit
   const unsigned grid = (unsigned)(b < resident ? b : resident);
   exchange_merge_kernel<<<grid, kXThreads, 0, st>>>(p);

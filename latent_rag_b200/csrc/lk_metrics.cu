@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kMetricWarps * 32) retrieval_metrics_kernel(
   __syncwarp();
   if (lane != 0) return;  // the sums below are sequential on purpose (left-to-right float64)
   for (int m = 0; m < n_metrics; ++m) {
-    int k = mk[m];
+    const int k_req = mk[m];  // the caller's cut-off: the ideal DCG keeps it even when fewer ids were retrieved
+    int k = k_req;
     if (k <= 0 || k > kr) k = kr;
     double v = 0.0;
     if (kind[m] == 0) {  // recall
@@ -61,7 +62,10 @@ __global__ void __launch_bounds__(kMetricWarps * 32) retrieval_metrics_kernel(
       double dcg = 0.0, idcg = 0.0;
       for (int j = 0; j < k; ++j)
         if (r[j] >= 0) dcg += hit[j] ? disc[j] : 0.0;
-      const int64_t ni = n_rel < k ? n_rel : k;
+      // idcg runs over min(len(relevant), k) with the ORIGINAL k (retrieval_metrics.py:29), which may
+      // exceed the retrieved length: disc holds max(n_retrieved, largest cut-off) entries
+      const int64_t kk = k_req > 0 ? k_req : kr;
+      const int64_t ni = n_rel < kk ? n_rel : kk;
       for (int64_t j = 0; j < ni; ++j) idcg += disc[j];
       v = idcg != 0.0 ? dcg / idcg : 0.0;
     }

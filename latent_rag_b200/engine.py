@@ -98,7 +98,8 @@ class ExactIndex:
 
     def reserve(self, capacity: int) -> None:
         if capacity > self.capacity:
-            nat.check(self._lib.lk_index_reserve(self._h, int(capacity)), "lk_index_reserve")
+            nat.check(self._lib.lk_index_reserve(self._h, int(capacity), c_void_p(_stream(self.device))),
+                      "lk_index_reserve")
             self.capacity = int(capacity)
 
     def add(self, rows: ArrayLike) -> None:
@@ -143,7 +144,10 @@ class ExactIndex:
         if q.dim() != 2 or q.size(1) != self.dim:
             raise ValueError(f"expected [b, {self.dim}] queries, got {tuple(q.shape)}")
         if not 1 <= k <= nat.LK_MAX_K:
-            raise ValueError(f"k={k} outside 1..{nat.LK_MAX_K}")
+            # known incompatibility: the reference ranks a materialised [B, N] matrix and so
+            # takes any k (retrieval/bruteforce.py:81-82); the engine's deepest search is LK_MAX_K
+            raise ValueError(f"top-k of {k} is outside 1..{nat.LK_MAX_K} (LK_MAX_K), the deepest search the B200 "
+                             "engine runs; ask for fewer neighbours or search row slabs and merge them with merge_topk")
         b = q.size(0)
         ptr, dtype, mem, keep = _triple(q, self.device)
         if device_out:
@@ -174,16 +178,31 @@ class ExactIndex:
         nat.check(self._lib.lk_index_storage_bytes(self._h, byref(tb), byref(sb)), "lk_index_storage_bytes")
         tiles = np.empty(tb.value, dtype=np.uint8)
         side = np.empty(sb.value // 4, dtype=np.float32)
-        nat.check(self._lib.lk_index_export(self._h, c_void_p(tiles.ctypes.data), c_void_p(side.ctypes.data)),
-                  "lk_index_export")
+        nat.check(self._lib.lk_index_export(self._h, c_void_p(tiles.ctypes.data), c_void_p(side.ctypes.data),
+                                            c_void_p(_stream(self.device))), "lk_index_export")
         return tiles, side
 
     def import_bytes(self, tiles: np.ndarray, side: np.ndarray, n_rows: int) -> None:
         tiles = np.ascontiguousarray(tiles, dtype=np.uint8)
         side = np.ascontiguousarray(side, dtype=np.float32)
+        n_rows = int(n_rows)
+        want_t, want_s = self.image_bytes(n_rows)
+        if n_rows < 0 or tiles.nbytes != want_t or side.nbytes != want_s:
+            raise ValueError(f"index image does not hold {n_rows} rows of dim {self.dim}: {tiles.nbytes} tile bytes "
+                             f"(need {want_t}), {side.nbytes} side bytes (need {want_s})")
         self.reserve(n_rows)
-        nat.check(self._lib.lk_index_import(self._h, c_void_p(tiles.ctypes.data), c_void_p(side.ctypes.data),
-                                            int(n_rows)), "lk_index_import")
+        nat.check(self._lib.lk_index_import(self._h, c_void_p(tiles.ctypes.data), int(tiles.nbytes),
+                                            c_void_p(side.ctypes.data), int(side.nbytes), n_rows,
+                                            c_void_p(_stream(self.device))), "lk_index_import")
+
+    def image_bytes(self, n_rows: int) -> Tuple[int, int]:
+        """(tile bytes, side bytes) of the persisted image of `n_rows` rows: whole 128-row blocks of
+        K blocks of 128 bytes per row (include/latentknn.h, lk_index_storage_bytes)."""
+        elem = 2 if self.storage == "bf16" else 4
+        per_kb = 128 // elem
+        kblocks = -(-self.dim // per_kb)
+        nblk = -(-max(0, int(n_rows)) // 128)
+        return nblk * kblocks * 128 * 128, nblk * 128 * 4
 
 
 def merge_topk(cand_scores: ArrayLike, cand_idx: ArrayLike, k: int, device: int = 0):

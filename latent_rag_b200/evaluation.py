@@ -70,7 +70,9 @@ def evaluate_retrieval(retrieved_batch, relevant_batch, metrics: Optional[List[s
     dev = torch.device(f"cuda:{device}")
     ret, off, rel = _encode(retrieved_batch, relevant_batch)
     q, kr = ret.shape
-    disc = 1.0 / np.log2(np.arange(kr, dtype=np.int64) + 2)  # the reference's own discounts, float64
+    # the reference's own discounts, float64; the ideal DCG of "ndcg@k" sums min(len(relevant), k) of
+    # them with the caller's k, which can exceed the retrieved length (retrieval_metrics.py:29)
+    disc = 1.0 / np.log2(np.arange(max([kr] + ks), dtype=np.int64) + 2)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d_ret, d_off, d_rel, d_disc = t(ret), t(off), t(rel), t(disc)
     d_kind, d_k = t(np.asarray(kinds, dtype=np.int32)), t(np.asarray(ks, dtype=np.int32))

@@ -11,6 +11,7 @@ of their recall).  Anything else raises the reference's ValueError.
 from __future__ import annotations
 
 import json
+import os
 import time
 from pathlib import Path
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -98,30 +99,53 @@ class FAISSEmbeddingRetriever(BatchedRetrieveMixin):
         self.meta_fp = dict(meta.get("fingerprint", {}))
 
     def _save_index(self) -> None:
-        """Own on-disk image: magic, JSON header, raw tiles, raw side values."""
+        """Own on-disk image: magic, JSON header, raw tiles, raw side values.  Written to a
+        temporary file and renamed into place, so a crash mid-save never leaves a truncated image
+        under the index path."""
         tiles, side = self.index.export_bytes()
         header = json.dumps({"d": self.d, "n": self.index.size, "precision": self.precision,
                              "tile_bytes": int(tiles.nbytes), "side_bytes": int(side.nbytes)}).encode()
         self.path.parent.mkdir(parents=True, exist_ok=True)
-        with self.path.open("wb") as f:
-            f.write(_MAGIC)
-            f.write(len(header).to_bytes(8, "little"))
-            f.write(header)
-            f.write(tiles.tobytes())
-            f.write(side.tobytes())
+        tmp = self.path.with_name(self.path.name + f".tmp{os.getpid()}")
+        try:
+            with tmp.open("wb") as f:
+                f.write(_MAGIC)
+                f.write(len(header).to_bytes(8, "little"))
+                f.write(header)
+                f.write(tiles.tobytes())
+                f.write(side.tobytes())
+                f.flush()
+                os.fsync(f.fileno())
+            os.replace(tmp, self.path)
+        finally:
+            if tmp.exists():
+                tmp.unlink()
 
     def _load_index(self) -> None:
+        """Raises ValueError on anything that is not a complete image of this geometry (the
+        constructor then starts clean, FAISSEmbeddingRetriever.py:70-73): the header is never
+        trusted further than the bytes actually present."""
         with self.path.open("rb") as f:
             if f.read(8) != _MAGIC:
                 raise ValueError("not a latentknn index file")
             hlen = int.from_bytes(f.read(8), "little")
+            if not 0 < hlen <= 1 << 20:
+                raise ValueError("corrupt index header")
             hdr = json.loads(f.read(hlen))
             if hdr["d"] != self.d or hdr["precision"] != self.precision:
                 raise ValueError("index file does not match this retriever")
-            tiles = np.frombuffer(f.read(hdr["tile_bytes"]), dtype=np.uint8)
-            side = np.frombuffer(f.read(hdr["side_bytes"]), dtype=np.float32)
-        self.index = self._build_index(self.d, self.index_type)
-        self.index.import_bytes(tiles, side, int(hdr["n"]))
+            n = int(hdr["n"])
+            index = self._build_index(self.d, self.index_type)
+            want_t, want_s = index.image_bytes(n)
+            if n < 0 or int(hdr["tile_bytes"]) != want_t or int(hdr["side_bytes"]) != want_s:
+                raise ValueError("index header is inconsistent (rows vs payload sizes)")
+            tiles = np.frombuffer(f.read(want_t), dtype=np.uint8)
+            side_raw = f.read(want_s)
+            if tiles.nbytes != want_t or len(side_raw) != want_s:
+                raise ValueError("index file is truncated")
+            side = np.frombuffer(side_raw, dtype=np.float32)
+        index.import_bytes(tiles, side, n)  # checks the lengths again on both sides of the C ABI
+        self.index = index
 
     @staticmethod
     def _fingerprint(*, d: int, embedding_model: Optional[str], ae_type: Optional[str], latent_dim: Optional[int],

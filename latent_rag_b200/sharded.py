@@ -51,13 +51,16 @@ def distributed_precision(local_embeddings: torch.Tensor, group=None) -> np.ndar
 class ShardedRetriever:
     """One shard of a row-partitioned corpus; `search` returns the GLOBAL top-k on every rank.
 
-    local_embeddings  this rank's rows [n_local, D]
+    local_embeddings  this rank's rows [n_local, D], or an ExactIndex already holding them (a shard
+                      built chunk by chunk on the device; its metric / storage are kept)
     row_offset        global index of this rank's first row
     texts / doc_ids   optional GLOBAL lists for `retrieve` (host side, indexed by global row)
-    local_search      (queries, k) -> (scores [B,k], global ids [B,k]) torch tensors; default: the
-                      native engine on this rank's GPU.  Tests on CPU inject the oracle here.
-    merge             (cand_scores [B,W,k], cand_ids [B,W,k], k) -> (scores, ids); default: the
-                      native merge kernel.
+    local_search      TEST-ONLY seam: (queries, k) -> (scores [B,k], global ids [B,k]) torch tensors.
+                      The product path is the default -- the native engine on this rank's GPU; the
+                      gloo CPU tests (tests/test_dist_gloo.py) inject the oracle here to drive the
+                      host-side sharding / padding / exchange logic without a device.
+    merge             TEST-ONLY seam: (cand_scores [B,W,k], cand_ids [B,W,k], k) -> (scores, ids);
+                      default: the native merge kernel.
     """
 
     def __init__(
@@ -82,7 +85,12 @@ class ShardedRetriever:
         self.metric = metric
         self.group = group
         self.row_offset = int(row_offset)
-        self.n_local = int(local_embeddings.size(0))
+        prebuilt = None
+        if not torch.is_tensor(local_embeddings) and hasattr(local_embeddings, "search") and hasattr(local_embeddings, "size"):
+            prebuilt = local_embeddings  # an ExactIndex
+            if prebuilt.metric != metric:
+                raise ValueError(f"the prebuilt index is {prebuilt.metric}, not {metric}")
+        self.n_local = int(prebuilt.size if prebuilt is not None else local_embeddings.size(0))
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.texts = list(texts) if texts is not None else None
@@ -94,6 +102,10 @@ class ShardedRetriever:
         if local_search is not None:
             self._local_search = local_search
             self.comm_device = torch.device("cpu")
+        elif prebuilt is not None:
+            self.index = prebuilt
+            self.comm_device = torch.device(f"cuda:{prebuilt.device}")
+            self._local_search = self._native_local_search
         else:
             from .engine import ExactIndex  # needs the native library + a GPU
 
@@ -143,7 +155,10 @@ class ShardedRetriever:
 
     def search_tensors(self, queries: torch.Tensor, k: int):
         """Same as `search` but leaves the result where the merge produced it (CUDA tensors on
-        the native path: no host synchronisation)."""
+        the native path: no host synchronisation).  Nothing is checked here: a caller that consumes
+        these tensors must call `check()` at its own synchronisation point -- a search kernel whose
+        pipeline timed out or a peer that never published leaves id -1 / score -inf entries and is
+        reported there, not as an exception from this call."""
         if queries.dim() == 1:
             queries = queries.unsqueeze(0)
         b = queries.size(0)
@@ -182,6 +197,13 @@ class ShardedRetriever:
 
             out_d, out_i = merge_topk(cd, ci, k)
         return out_d, out_i
+
+    def check(self) -> None:
+        """Synchronise and raise if a search or an exchange since the last check timed out."""
+        if self.index is not None:
+            self.index.check()
+        if self._xchg is not None:
+            self._xchg.check()
 
     def retrieve(self, query_emb: torch.Tensor, top_k: int = 10):
         d, i = self.search(query_emb, top_k)

@@ -6,6 +6,8 @@ of test/test_evaluation.py:9-22 (recall 1/3, mrr 1/3, ndcg@3 0.23463936301137822
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 ID = Union[int, str]
@@ -27,9 +29,11 @@ def mrr(retrieved: Sequence[ID], relevant: Sequence[ID]) -> float:
 
 
 def ndcg_at_k(retrieved: Sequence[ID], relevant: Sequence[ID], k: int) -> float:
-    """retrieval_metrics.py:25-31: binary gains, log2(i+2) discount."""
-    dcg = sum(1.0 / math.log2(i + 2) for i, d in enumerate(retrieved[:k]) if d in relevant)
-    idcg = sum(1.0 / math.log2(i + 2) for i in range(min(len(relevant), k)))
+    """retrieval_metrics.py:25-31: binary gains, log2(i+2) discount.  numpy's log2 like the
+    reference (math.log2 differs from it in the last bit for some arguments), summed left to right
+    as Python floats, misses contributing 0.0."""
+    dcg = sum(1.0 / np.log2(i + 2) if d in relevant else 0.0 for i, d in enumerate(retrieved[:k]))
+    idcg = sum(1.0 / np.log2(i + 2) for i in range(min(len(relevant), k)))
     return dcg / idcg if idcg else 0.0
 
 

@@ -38,13 +38,15 @@ def bruteforce_build(embeddings: torch.Tensor, metric: str = "cosine") -> torch.
 
 
 def bruteforce_search(
-    emb: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "cosine"
+    emb: torch.Tensor, queries: torch.Tensor, k: int, metric: str = "cosine", chunk_bytes: int = _CHUNK_BYTES
 ) -> Tuple[np.ndarray, np.ndarray]:
     """bruteforce.py:58-83.  `emb` is the output of `bruteforce_build`.
 
     cosine   : scores = normalize(Q) @ emb.T                       (:66-69)
     euclidean: scores = -(|q|^2 + |e|^2 - 2 q.e)                   (:73-76)
     k = min(k, N); torch.topk sorted descending; numpy (D, I)      (:81-83)
+    chunk_bytes bounds the fp32 [b, N] score block (BASELINE.md section 3 times the CPU path with
+    8 GB blocks); results do not depend on it.
     """
     if queries.dim() == 1:
         queries = queries.unsqueeze(0)
@@ -56,7 +58,7 @@ def bruteforce_search(
     out_i = np.empty((b, k), dtype=np.int64)
     if b == 0:
         return out_d, out_i
-    step = max(1, min(b, _CHUNK_BYTES // max(1, 4 * n)))
+    step = max(1, min(b, int(chunk_bytes) // max(1, 4 * n)))
     if metric == "euclidean":
         e2 = (emb * emb).sum(dim=1).unsqueeze(0)
     for s in range(0, b, step):

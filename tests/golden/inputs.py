@@ -64,6 +64,17 @@ def metrics_case(q: int = 40, k: int = 10, universe: int = 60) -> Tuple[List[Lis
     return retrieved, relevant
 
 
+def metrics_ragged_case(q: int = 60, universe: int = 30) -> Tuple[List[List[int]], List[List[int]]]:
+    """Ragged retrieved lists (1..12 ids, shorter than the cut-off 10 for most) against 0..11 relevant
+    ids: covers len(retrieved) < k < len(relevant), where the ideal DCG keeps the caller's k
+    (evaluation/retrieval_metrics.py:29)."""
+    rng = np.random.default_rng(23)
+    retrieved = [rng.integers(0, universe, int(rng.integers(1, 13))).tolist() for _ in range(q)]
+    relevant = [rng.integers(0, universe, int(rng.integers(0, 12))).tolist() for _ in range(q)]
+    retrieved[0], relevant[0] = [4, 9, 1, 7, 3], [9, 3, 11, 12, 13, 14, 15, 16]
+    return retrieved, relevant
+
+
 def maxsim_case(q: int = 30, ck: int = 30, docs: int = 12, seed: int = 91):
     """Candidates of `q` queries for the document-level MaxSim aggregation (main.py:264-282):
     descending scores with some exact ties, chunk -> doc ids with repeats.

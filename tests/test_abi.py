@@ -48,7 +48,9 @@ def test_python_constants_match_the_header():
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.lk_abi_version() == 1
+    from latent_rag_b200 import _native
+
+    assert lib.lk_abi_version() == _native.LK_ABI_VERSION == 2
     assert isinstance(lib.lk_last_error(), bytes)
 
 
@@ -61,6 +63,10 @@ def test_bad_arguments_are_rejected_without_a_device(lib):
     assert lib.lk_index_search(None, None, 0, 0, 1, 5, None, None, 0, 0, 0, None) == -1
     assert lib.lk_merge_topk(0, None, None, 1, 0, 1, 1, None, None, 0, None) == -1
     assert lib.lk_index_search(None, None, 0, 0, 1, 5000, None, None, 0, 0, 0, None) == -1  # k past LK_MAX_K
+    # a truncated persistence image is rejected by its length, never read: argument checks come first
+    assert lib.lk_index_import(None, None, 0, None, 0, 5, None) == -1
+    assert lib.lk_index_reserve(None, 10, None) == -1
+    assert lib.lk_index_export(None, None, None, None) == -1
     assert lib.lk_bert_create(ctypes.byref(h), 0, 100, 64, 128, 4, 256, 2, 1e-12, None) == -1  # no weights
     assert lib.lk_bert_encode(None, None, None, 0, 1, 8, 1, None, 0, None) == -1
     assert lib.lk_linear_forward(0, None, 4, 64, None, 128, None, None, 0, 0, None) == -1

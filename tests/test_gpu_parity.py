@@ -446,6 +446,67 @@ def test_faiss_index_persistence(lrb, tmp_path):
     assert r2.index.size == 50 and len(r2._texts) == 50
 
 
+def test_truncated_or_corrupt_index_file_starts_clean(lrb, tmp_path):
+    """a truncated image (a crash mid-save) or a header that lies about its payload must
+    take the reference's 'corrupted file -> start clean' route (FAISSEmbeddingRetriever.py:70-73),
+    never reach the device copy; saves go through a temporary file."""
+    emb = inputs.reference_test_embeddings(300, 48)
+    texts = [f"chunk_{j}" for j in range(300)]
+    path = tmp_path / "idx.faiss"
+    r1 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    r1.build(emb, texts, list(range(300)), train=False)
+    assert not list(tmp_path.glob("*.tmp*"))
+    blob = path.read_bytes()
+    path.write_bytes(blob[: len(blob) // 2])            # truncated
+    r2 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    assert r2.index.size == 0 and r2._texts == []
+    hlen = int.from_bytes(blob[8:16], "little")
+    lying = blob[:16] + blob[16:16 + hlen].replace(b'"n": 300', b'"n": 900') + blob[16 + hlen:]
+    path.write_bytes(lying)                              # header rows vs payload sizes disagree
+    r3 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    assert r3.index.size == 0
+    # the raw ABI rejects a short buffer by its length
+    ix = lrb.ExactIndex(48, 300, metric="cosine")
+    tiles, side = r1.index.export_bytes()
+    with pytest.raises(ValueError):
+        ix.import_bytes(tiles[:-128], side, 300)
+    rc = ix._lib.lk_index_import(ix._h, tiles.ctypes.data, int(tiles.nbytes) - 128, side.ctypes.data, int(side.nbytes),
+                                 300, None)
+    assert rc == -1 and b"need" in ix._lib.lk_last_error()
+    ix.import_bytes(tiles, side, 300)
+    d, i = ix.search(emb[:5], 3)
+    d1, i1 = r1.index.search(emb[:5], 3)
+    np.testing.assert_array_equal(i, i1)
+    path.write_bytes(blob)
+    r4 = lrb.FAISSEmbeddingRetriever(embedding_dim=48, index_path=path, index_type="flatip")
+    assert r4.index.size == 300 and r4.retrieve(emb[7], top_k=1)[2] == [7]
+
+
+def test_adds_and_growth_on_a_side_stream(lrb):
+    """add / reserve / export are ordered on the caller's stream -- growing the index right
+    after an add on a non-blocking side stream must not lose the rows of that add."""
+    rng = np.random.default_rng(3)
+    emb = oracle.bf16_round(torch.from_numpy(rng.standard_normal((60_000, 128)).astype(np.float32)))
+    whole = lrb.ExactIndex(128, 60_000, metric="euclidean")
+    whole.add(emb)
+    d0, i0 = whole.search(emb[:64], 5)
+    for rep in range(3):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            ix = lrb.ExactIndex(128, 1024, metric="euclidean")  # grows several times
+            e_dev = emb.cuda()
+            s.wait_stream(torch.cuda.default_stream())
+            for lo in range(0, 60_000, 7_500):
+                ix.add(e_dev[lo:lo + 7_500])
+            tiles, side = ix.export_bytes()
+            d, i = ix.search(emb[:64], 5)
+        np.testing.assert_array_equal(i, i0)
+        np.testing.assert_array_equal(d, d0)
+        t0, s0 = whole.export_bytes()
+        np.testing.assert_array_equal(tiles, t0)
+        ix.close()
+
+
 def test_faiss_semantics(lrb):
     emb = inputs.reference_test_embeddings(3, 16)
     fr = lrb.FAISSEmbeddingRetriever(16, index_type="flatip")
@@ -729,6 +790,15 @@ def test_device_metrics_equal_the_reference_bit_for_bit(lrb, golden):
         assert abs(pq["nDCG@10"] - oracle.ndcg_at_k(r, l, 10)) < 1e-15
     with pytest.raises(ValueError):
         lrb.evaluate_retrieval(ret, rel, ["precision@5"])
+    # fewer retrieved ids than the cut-off, more relevant ones than retrieved -- the ideal DCG
+    # runs over min(len(relevant), k) with the caller's k (retrieval_metrics.py:29), not the retrieved length
+    # (per-query values of the reference itself: tests/golden/make_golden.py::metrics, "ragged_per_query")
+    rr, rl = inputs.metrics_ragged_case()
+    got, pq = lrb.evaluate_retrieval(rr, rl, ["ndcg@10", "ndcg@3", "recall@10", "mrr"], return_per_query=True)
+    for t, one in enumerate(pq):
+        for name in ("ndcg@10", "ndcg@3", "recall@10", "mrr"):
+            assert one[name] == g["ragged_per_query"][name][t], (t, name)
+    assert pq[0]["ndcg@10"] < (1 / np.log2(3) + 1 / np.log2(6)) / sum(1 / np.log2(j + 2) for j in range(5))
 
 
 def test_rank_positive_matches_reference_outputs(lrb):

@@ -101,12 +101,19 @@ def test_oracle_metrics_kats_and_reference_outputs():
     # test/test_evaluation.py:9-22
     assert oracle.recall_at_k([1, 2, 3, 4, 5], [3, 4, 6], 3) == 1 / 3 == g["kat"]["recall_at_3"]
     assert oracle.mrr([1, 2, 3, 4, 5], [3, 4, 6]) == 1 / 3 == g["kat"]["mrr"]
-    assert abs(oracle.ndcg_at_k([1, 2, 3, 4, 5], [3, 4, 6], 3) - 0.23463936301137822) < 1e-12
+    assert oracle.ndcg_at_k([1, 2, 3, 4, 5], [3, 4, 6], 3) == g["kat"]["ndcg_at_3"]
+    assert abs(g["kat"]["ndcg_at_3"] - 0.23463936301137822) < 1e-15
     retrieved, relevant = inputs.metrics_case()
     res = oracle.evaluate_retrieval(retrieved, relevant, list(g["evaluate_retrieval"]))
     for name, ref in g["evaluate_retrieval"].items():
         assert abs(res[name]["mean"] - ref["mean"]) < 1e-12
         assert abs(res[name]["std"] - ref["std"]) < 1e-12
+    # per-query values of the reference on ragged lists (len(retrieved) < k < len(relevant) included): bit for bit
+    rr, rl = inputs.metrics_ragged_case()
+    rg = g["ragged_per_query"]
+    for t, (r, l) in enumerate(zip(rr, rl)):
+        assert oracle.ndcg_at_k(r, l, 10) == rg["ndcg@10"][t] and oracle.ndcg_at_k(r, l, 3) == rg["ndcg@3"][t]
+        assert oracle.recall_at_k(r, l, 10) == rg["recall@10"][t] and oracle.mrr(r, l) == rg["mrr"][t]
 
 
 def test_mahalanobis_oracle_self_consistency():
