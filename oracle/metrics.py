@@ -58,8 +58,8 @@ def _one(retrieved, relevant, name: str, k: Optional[int]) -> float:
 def evaluate_retrieval(
     retrieved_batch: List[Sequence[ID]], relevant_batch: List[Sequence[ID]], metrics: List[str]
 ) -> Dict[str, Dict[str, float]]:
-    """retrieval_metrics.py:55-96, batch form: per metric the mean and the sample
-    standard deviation (ddof=1; 0.0 for a single query)."""
+    """retrieval_metrics.py:55-96, batch form: per metric np.mean and the sample standard
+    deviation np.std(ddof=1) (0.0 for a single query)."""
     assert len(retrieved_batch) == len(relevant_batch)
     if not metrics:
         raise ValueError("No metrics specified.")
@@ -68,9 +68,8 @@ def evaluate_retrieval(
     for m in metrics:
         name, k = _parse(m)
         vals = [_one(r, rel, name, k) for r, rel in zip(retrieved_batch, relevant_batch)]
-        mean = sum(vals) / q
-        std = math.sqrt(sum((v - mean) ** 2 for v in vals) / (q - 1)) if q > 1 else 0.0
-        out[m] = {"mean": float(mean), "std": float(std)}
+        # numpy's (pairwise) mean and std like retrieval_metrics.py:85-88, so the summary is the reference's bit for bit
+        out[m] = {"mean": float(np.mean(vals)), "std": float(np.std(vals, ddof=1)) if q > 1 else 0.0}
     return out
 
 
