@@ -70,7 +70,17 @@ struct lk_index {
   int* ticket = nullptr;  // completion counters of the single-launch small-batch search
   unsigned char* pin = nullptr;  // pinned, device-visible host staging of that path: queries | scores | ids
   size_t pin_cap = 0;
-  Buf stage, white, q_tiles, q_side, part_s, part_i, part_c, out_s, out_i, debug;
+  // fp32 storage on the tensor cores: split-bf16 planes of the rows (x = hi + lo), built lazily from the fp32
+  // tiles by the first tcgen05 search and extended as rows are added; the fp32 tiles stay (exact FMA kernel)
+  TileGeom gp;                    // geometry of the planes: kblocks = 2 * ceil(dim / 64)
+  unsigned char* planes = nullptr;
+  int64_t planes_blocks = 0;      // row blocks allocated
+  int64_t planes_rows = 0;        // rows converted so far
+  // what the search kernels of the current call read: the tiles as stored, or the planes
+  const unsigned char* sv_tiles = nullptr;
+  TileGeom sv_g;
+  int sv_split = 0;
+  Buf stage, white, q_tiles, q_side, q_planes, part_s, part_i, part_c, out_s, out_i, debug;
   Buf deep_s, deep_i, deep_last, deep_flags, deep_tiles, deep_side;  // slab search (k > 128)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -116,7 +126,8 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->err_flag) cudaFree(ix->err_flag);
   if (ix->ticket) cudaFree(ix->ticket);
   if (ix->pin) cudaFreeHost(ix->pin);
-  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->part_s, &ix->part_i, &ix->part_c,
+  if (ix->planes) cudaFree(ix->planes);
+  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->q_planes, &ix->part_s, &ix->part_i, &ix->part_c,
                  &ix->out_s, &ix->out_i, &ix->debug, &ix->deep_s, &ix->deep_i, &ix->deep_last, &ix->deep_flags,
                  &ix->deep_tiles, &ix->deep_side};
   for (Buf* b : bufs) b->release();
@@ -159,6 +170,8 @@ int lk_index_create(lk_index** out, int device, int64_t capacity_rows, int dim, 
   ix->kmetric = metric == LK_COSINE ? LK_COSINE : LK_EUCLIDEAN;
   ix->storage = storage;
   ix->g = make_geom(dim, storage);
+  ix->gp = make_geom(dim, LK_BF16);
+  ix->gp.kblocks *= 2;  // [hi plane | lo plane]
   ix->capacity = capacity_rows;
   ix->side_mode = ix->kmetric == LK_COSINE ? 0 : 1;
   ix->prenorm = (ix->kmetric == LK_COSINE && storage == LK_F32) ? 1 : 0;
@@ -286,6 +299,9 @@ int lk_index_reserve(lk_index* ix, int64_t capacity_rows, void* stream) {
   }
   cudaFree(ix->tiles);
   cudaFree(ix->side);
+  if (ix->planes) cudaFree(ix->planes);  // rebuilt from the new tiles by the next tensor-core search
+  ix->planes = nullptr;
+  ix->planes_blocks = ix->planes_rows = 0;
   ix->tiles = tiles;
   ix->side = side;
   ix->capacity = capacity_rows;
@@ -366,12 +382,42 @@ int lk_index_check(lk_index* ix) {
   return LK_OK;
 }
 
-static int pick_kernel(const lk_index* ix, int requested, int k) {
+// the geometry the tcgen05 kernel would read for this index: the bf16 tiles, or the split-bf16 planes of fp32 rows
+static const TileGeom& umma_geom(const lk_index* ix) { return ix->storage == LK_BF16 ? ix->g : ix->gp; }
+
+static int pick_kernel(const lk_index* ix, int requested, int k, int64_t b) {
   const char* env = getenv("LK_FORCE_KERNEL");
   if (env && !strcmp(env, "simt")) requested = LK_KERNEL_SIMT;
   if (env && !strcmp(env, "umma")) requested = LK_KERNEL_UMMA;
-  if (requested == LK_KERNEL_AUTO) return umma_supported(ix->g, k) ? LK_KERNEL_UMMA : LK_KERNEL_SIMT;
+  if (requested == LK_KERNEL_AUTO) {
+    if (!umma_supported(umma_geom(ix), k)) return LK_KERNEL_SIMT;
+    // fp32 storage: the exact FMA kernel for tiny problems (no planes to build, bit-faithful fp32 products),
+    // the tensor cores on split-bf16 planes (x = hi + lo, three MMAs per product) from ~1 M scores on
+    if (ix->storage == LK_F32 && b * ix->n_rows < (1 << 20)) return LK_KERNEL_SIMT;
+    return LK_KERNEL_UMMA;
+  }
   return requested;
+}
+
+// fp32 storage, tensor-core search: make the planes cover every row added so far
+static int ensure_planes(lk_index* ix, cudaStream_t st) {
+  const int64_t need_blocks = alloc_blocks(ix->capacity);
+  if (!ix->planes || ix->planes_blocks < need_blocks) {
+    if (ix->planes) cudaFree(ix->planes);
+    ix->planes = nullptr;
+    ix->planes_rows = ix->planes_blocks = 0;
+    LK_CUDA(cudaMalloc((void**)&ix->planes, (size_t)need_blocks * ix->gp.block_bytes()));
+    ix->planes_blocks = need_blocks;
+  }
+  if (ix->planes_rows < ix->n_rows) {
+    // whole row blocks, from the block the first new row lives in to the (pair-aligned) last: rows that do
+    // not exist yet are zeros in the fp32 tiles and NaN-sided, so they convert to zeros and never rank
+    const int64_t blk0 = ix->planes_rows / kBlockRows, blk1 = alloc_blocks(ix->n_rows);
+    int rc = launch_planes_from_tiles(ix->tiles, ix->g, blk0, blk1 - blk0, ix->gp, ix->planes, st);
+    if (rc != LK_OK) return rc;
+    ix->planes_rows = ix->n_rows;
+  }
+  return LK_OK;
 }
 
 
@@ -384,7 +430,8 @@ static SearchArgs rows_args(const lk_index* ix, const unsigned char* tiles, cons
   a.tiles = tiles;
   a.side = side;
   a.n_rows = n_rows;
-  a.g = ix->g;
+  a.g = ix->sv_g;
+  a.split_n = ix->sv_split;
   a.q_tiles = q_tiles;
   a.q_side = q_side;
   a.n_queries = b;
@@ -498,7 +545,7 @@ static int deep_search(lk_index* ix, int which, const unsigned char* q_tiles, co
   constexpr int64_t kUnit = 2 * kBlockRows;
   int rc;
   const int64_t n = ix->n_rows, n_units = (n + kUnit - 1) / kUnit;
-  const int64_t block_bytes = ix->g.block_bytes();
+  const int64_t block_bytes = ix->sv_g.block_bytes();
   int64_t want = 2 * ((k + kMaxK - 1) / kMaxK);
   if (want > n_units) want = n_units;
   const int64_t upu = (n_units + want - 1) / want;  // units per slab
@@ -527,7 +574,7 @@ static int deep_search(lk_index* ix, int which, const unsigned char* q_tiles, co
       L.query_stride = kMaxK;
       for (int64_t g = g0; g < g1; ++g) {
         const Slab& s = work[(size_t)g];
-        const unsigned char* tiles = ix->tiles + (s.row0 / kBlockRows) * block_bytes;
+        const unsigned char* tiles = ix->sv_tiles + (s.row0 / kBlockRows) * block_bytes;
         const float* side = ix->side + s.row0;
         if (s.block) {  // [the block][a padding block: zero rows, NaN side values]
           if (ix->deep_tiles.p == nullptr) {
@@ -597,15 +644,27 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
   }
   if (b == 0) return LK_OK;
   const bool deep = k > kMaxK;  // slab search: every fused search below asks for kMaxK
-  const int which = pick_kernel(ix, kernel, deep ? kMaxK : k);
-  if (which == LK_KERNEL_UMMA && !umma_supported(ix->g, deep ? kMaxK : k)) {
-    set_error("lk_index_search: the tcgen05 kernel needs bf16 storage (k=%d, storage=%d)", k,
+  const int which = pick_kernel(ix, kernel, deep ? kMaxK : k, b);
+  if (which == LK_KERNEL_UMMA && !umma_supported(umma_geom(ix), deep ? kMaxK : k)) {
+    set_error("lk_index_search: the tcgen05 kernel does not take this shape (dim=%d, k=%d, storage=%d)", ix->dim, k,
               ix->storage);
     return LK_ERR_UNSUPPORTED;
   }
   DeviceGuard guard(ix->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc;
+  // what the search kernels read: the tiles as stored, or -- fp32 storage on the tensor cores -- the planes
+  const bool split = which == LK_KERNEL_UMMA && ix->storage == LK_F32;
+  if (split) {
+    if ((rc = ensure_planes(ix, st)) != LK_OK) return rc;
+    ix->sv_tiles = ix->planes;
+    ix->sv_g = ix->gp;
+    ix->sv_split = ix->gp.kblocks / 2;
+  } else {
+    ix->sv_tiles = ix->tiles;
+    ix->sv_g = ix->g;
+    ix->sv_split = 0;
+  }
 
   if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[0], st));
 
@@ -696,10 +755,16 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     if (atoi(e) & 8) LK_CUDA(cudaMemsetAsync(ix->q_tiles.p, 0x7F, qt_bytes, st));  // test aid: huge garbage
   rc = ingest_rows(ix, queries, q_dtype, q_mem, b, ix->q_tiles.p, ix->q_side.as<float>(), 0, st);
   if (rc != LK_OK) return rc;
+  const unsigned char* q_view = ix->q_tiles.as<unsigned char>();
+  if (split) {  // the query tiles as planes, like the rows
+    if ((rc = ix->q_planes.ensure((size_t)(b_pad / kBlockRows) * ix->gp.block_bytes())) != LK_OK) return rc;
+    rc = launch_planes_from_tiles(ix->q_tiles.p, ix->g, 0, b_pad / kBlockRows, ix->gp, ix->q_planes.p, st);
+    if (rc != LK_OK) return rc;
+    q_view = ix->q_planes.as<unsigned char>();
+  }
 
   // 2.-4. plan, fused distance + selection, merge of the partial lists
-  const SearchArgs a = rows_args(ix, ix->tiles, ix->side, ix->n_rows, ix->q_tiles.as<unsigned char>(),
-                                 ix->q_side.as<float>(), b, k);
+  const SearchArgs a = rows_args(ix, ix->sv_tiles, ix->side, ix->n_rows, q_view, ix->q_side.as<float>(), b, k);
   const char* dump_path = which == LK_KERNEL_UMMA && !deep ? getenv("LK_UMMA_DUMP") : nullptr;
   const int64_t seed_rows = which == LK_KERNEL_UMMA && !deep ? umma_seed_rows(a, ix->sm_count) : 0;
   // results land here: the caller's device buffers; for host outputs a device staging buffer, or --
@@ -733,7 +798,7 @@ int lk_index_search(lk_index* ix, const void* queries, int q_dtype, int q_mem, i
     if (ix->timing) LK_CUDA(cudaEventRecord(ix->ev[1], st));
     for (int64_t q0 = 0; q0 < b; q0 += kDeepChunk) {
       const int64_t bc = b - q0 < kDeepChunk ? b - q0 : kDeepChunk;
-      rc = deep_search(ix, which, ix->q_tiles.as<unsigned char>() + (q0 / kBlockRows) * ix->g.block_bytes(),
+      rc = deep_search(ix, which, q_view + (q0 / kBlockRows) * ix->sv_g.block_bytes(),
                        ix->q_side.as<float>() + q0, bc, k, idx_base, d_s + q0 * k, d_i + q0 * k, st);
       if (rc != LK_OK) return rc;
     }
@@ -964,7 +1029,15 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
       if ((rc = ae->zout.ensure((size_t)step * ae->d_latent * 4)) != LK_OK) return rc;
       zdev = ae->zout.as<float>();
     }
-    if (use_umma) {
+    const char* pe = getenv("LK_AE_PAIR");  // bring-up override: 0 = the single-CTA kernel for bf16 operands too
+    const bool use_pair = use_umma && ae->precision == LK_BF16 && !(pe && !atoi(pe)) &&
+                          ae_pair_supported(ae->d_in, ae->d_hidden, ae->d_latent, ae->sm_count) &&
+                          (reinterpret_cast<uintptr_t>(xin) & 31u) == 0;
+    if (use_pair) {
+      // bf16 operands: CTA pairs, the fp32 rows are rounded inside the kernel (no split pass)
+      rc = launch_ae_pair(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs, ae->w1_slabs, ae->b0, ae->b1, l2,
+                          zdev, ae->err_flag, ae->sm_count, st);
+    } else if (use_umma) {
       if ((rc = ae->xslabs.ensure(ae_umma_x_slab_bytes(step, ae->d_in))) != LK_OK) return rc;
       const int planes = ae->precision == LK_BF16 ? 1 : 2;
       if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, planes, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;

@@ -89,6 +89,11 @@ struct TileGeom {
 int launch_tile_rows(const void* rows, int rows_dtype, int64_t n, const TileGeom& g, void* tiles,
                      float* side, int64_t row0, int side_mode, int prenorm, cudaStream_t st);
 
+// fp32 tiles (geometry g32: 32 elements per K block) of row blocks [blk0, blk0 + n_blocks) -> split-bf16 planes
+// (geometry gp: per row block [hi plane | lo plane], gp.kblocks / 2 K blocks of 64 each; x = hi + lo to 2^-17)
+int launch_planes_from_tiles(const void* tiles32, const TileGeom& g32, int64_t blk0, int64_t n_blocks,
+                             const TileGeom& gp, void* planes, cudaStream_t st);
+
 // out[n, dim] fp32 = rows[n, dim] (fp32 or bf16) * L[dim, dim] (fp64, row-major), fp64 accumulate
 int launch_whiten(const void* rows, int rows_dtype, int64_t n, int dim, const double* L, float* out,
                   cudaStream_t st);
@@ -102,6 +107,8 @@ struct SearchArgs {
   const float* q_side;
   int64_t n_queries;
   int metric;              // LK_COSINE or LK_EUCLIDEAN (mahalanobis is whitened L2)
+  int split_n;             // tcgen05 kernel on fp32 storage: tiles / q_tiles are split-bf16 PLANES, [hi | lo] slabs
+                           // of split_n K blocks each per row block (g.kblocks = 2 * split_n); 0 = plain bf16 tiles
   int k;                   // requested k
   int ksel;                // entries per partial list (>= k)
   int n_lists;             // partial lists per query (stride of the partial arrays)
@@ -170,6 +177,12 @@ int launch_ae_split_rows(const float* x, int64_t m, int d_in, int n_planes, unsi
 int launch_ae_umma(const unsigned char* x_slabs, int64_t m, int d_in, int d_hidden, int d_latent,
                    const unsigned char* w0_slabs, const unsigned char* w1_slabs, const float* b0, const float* b1,
                    int l2norm, int n_planes, float* z, int* err_flag, int sm_count, cudaStream_t st);
+
+// bf16-operand encoder on CTA pairs, fp32 rows converted in the kernel (lk_ae_pair.cu); weight slabs as above
+int ae_pair_supported(int d_in, int d_hidden, int d_latent, int sm_count);
+int launch_ae_pair(const float* x, int64_t m, int d_in, int d_hidden, int d_latent, const unsigned char* w0_slabs,
+                   const unsigned char* w1_slabs, const float* b0, const float* b1, int l2norm, float* z, int* err_flag,
+                   int sm_count, cudaStream_t st);
 
 // linear layer Y = act(X W^T + b) (+ R) on tcgen05 (lk_gemm_umma.cu): X / W as split-bf16 slab planes
 // (launch_ae_split_rows / ae_umma_weight_slabs with 128-row slabs), n % 128 == 0, k % 64 == 0

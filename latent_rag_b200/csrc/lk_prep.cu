@@ -74,6 +74,41 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(const InT* __restrict__ 
   }
 }
 
+// fp32 tiles -> split-bf16 planes of the same rows.  One warp per row; a lane converts 8 consecutive
+// elements (two fp32 chunks -> one bf16 chunk per plane) per step.
+__global__ void __launch_bounds__(256) planes_from_tiles_kernel(const unsigned char* __restrict__ t32, int kblocks32,
+                                                                int64_t block_bytes32, int64_t blk0, int64_t n_rows,
+                                                                int n_kb, int64_t block_bytes_p,
+                                                                unsigned char* __restrict__ planes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int64_t blk = blk0 + r / kBlockRows;
+  const int rin = (int)(r % kBlockRows);
+  const unsigned char* src = t32 + blk * block_bytes32;
+  unsigned char* dst = planes + blk * block_bytes_p;
+  for (int kc = lane; kc < n_kb * 8; kc += 32) {  // bf16 chunk kc = elements 8 kc .. 8 kc + 7
+    float x[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c4 = kc * 2 + h;  // fp32 chunk (4 elements): K block c4 >> 3, logical chunk c4 & 7
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((c4 >> 3) < kblocks32)
+        v = *reinterpret_cast<const float4*>(src + (int64_t)(c4 >> 3) * kSlabBytes + slab_chunk_offset(rin, c4 & 7));
+      x[4 * h] = v.x; x[4 * h + 1] = v.y; x[4 * h + 2] = v.z; x[4 * h + 3] = v.w;
+    }
+    alignas(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = __float2bfloat16_rn(x[e]);
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
+    }
+    const int64_t off = (int64_t)(kc >> 3) * kSlabBytes + slab_chunk_offset(rin, kc & 7);
+    *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + (int64_t)n_kb * kSlabBytes + off) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // out[r][j] = sum_i x[r][i] * L[i][j], fp64 accumulate.  CTA = 128 threads, 8 rows.
 template <typename InT>
 __global__ void __launch_bounds__(128) whiten_kernel(const InT* __restrict__ rows, int64_t n, int dim,
@@ -119,6 +154,18 @@ int launch_tile_rows(const void* rows, int rows_dtype, int64_t n, const TileGeom
   }
 #undef LK_TILE
   LK_CHECK_LAUNCH("tile_rows_kernel");
+  return LK_OK;
+}
+
+int launch_planes_from_tiles(const void* tiles32, const TileGeom& g32, int64_t blk0, int64_t n_blocks,
+                             const TileGeom& gp, void* planes, cudaStream_t st) {
+  if (n_blocks <= 0) return LK_OK;
+  const int64_t n_rows = n_blocks * kBlockRows;
+  const unsigned grid = (unsigned)((n_rows + 7) / 8);
+  planes_from_tiles_kernel<<<grid, 256, 0, st>>>(static_cast<const unsigned char*>(tiles32), g32.kblocks,
+                                                 g32.block_bytes(), blk0, n_rows, gp.kblocks / 2, gp.block_bytes(),
+                                                 static_cast<unsigned char*>(planes));
+  LK_CHECK_LAUNCH("planes_from_tiles_kernel");
   return LK_OK;
 }
 

@@ -71,7 +71,10 @@ struct UmmaParams {
   int64_t n_queries;
   int64_t total_units;   // n_qt * nblk
   int nblk;              // row-block PAIRS in the corpus (units per query tile)
-  int nkb;               // K blocks of 64 per row
+  int nkb;               // K blocks of 64 the MMA loop runs over per unit (split mode: 3 * split_n)
+  int nkb_q;             // K-block slabs of a query tile in memory (= nkb; split mode: 2 * split_n)
+  int split_n;           // 0, or the K blocks per PLANE of split-bf16 operands (fp32 storage): rows and queries
+                         // are stored as [hi plane | lo plane] and step kb multiplies q(hi,hi,lo) by e(hi,lo,hi)
   int n_stages;
   int n_lists;
   int64_t block_bytes;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   float* side_ring = reinterpret_cast<float*>(smem + kBarBytes);
   unsigned char* q_sm = smem + kHeaderBytes;
   q_sm += (1024u - (ptx::smem_u32(q_sm) & 1023u)) & 1023u;  // swizzle atoms are 1024-byte aligned
-  unsigned char* stage_sm = q_sm + (QRES ? p.nkb * kKBlockBytes : 0);
+  unsigned char* stage_sm = q_sm + (QRES ? p.nkb_q * kKBlockBytes : 0);
   constexpr int kSlabsPerStage = kUnitBlocks / CG;  // corpus row blocks this CTA loads per K block
   constexpr int kStageBytes = (QRES ? kSlabsPerStage : kSlabsPerStage + 1) * kKBlockBytes;
 
@@ -162,6 +165,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   const int rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;  // 0 = leader
   const int64_t G = gridDim.x / CG, c = blockIdx.x / CG;        // scheduling groups, this CTA's group
   const int64_t u0 = unit_begin(c, p.total_units, G), u1 = unit_begin(c + 1, p.total_units, G);
+  // split-bf16 operands (x = hi + lo, fp32-level products as hi*hi + hi*lo + lo*hi): K step kb of the
+  // tripled loop reads corpus slab e_kb(kb) = (hi.., lo.., hi..) and query slab q_kb(kb) = (hi.., hi.., lo..)
+  auto e_kb = [&](int kb) { return p.split_n && kb >= 2 * p.split_n ? kb - 2 * p.split_n : kb; };
+  auto q_kb = [&](int kb) { return p.split_n && kb >= p.split_n ? kb - p.split_n : kb; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
@@ -221,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           break;
         }
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(p.nkb * kKBlockBytes));
-          for (int kb = 0; kb < p.nkb; ++kb)
+          ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(p.nkb_q * kKBlockBytes));
+          for (int kb = 0; kb < p.nkb_q; ++kb)
             ptx::bulk_g2s(ptx::smem_u32(q_sm + kb * kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
                           kKBlockBytes, qfull_bar);
         }
@@ -241,12 +248,12 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
 #pragma unroll
           for (int h = 0; h < kSlabsPerStage; ++h) {  // rows 0-127 and 128-255 of the N=256 operand (CG=2: this CTA's half)
-            const unsigned char* src = e_src + (h + rank * kSlabsPerStage) * p.block_bytes + (int64_t)kb * kKBlockBytes;
+            const unsigned char* src = e_src + (h + rank * kSlabsPerStage) * p.block_bytes + (int64_t)e_kb(kb) * kKBlockBytes;
             if (stream_once) ptx::bulk_g2s_hint(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx), stream_policy);
             else ptx::bulk_g2s(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx));
           }
           if (!QRES)
-            ptx::bulk_g2s(dst + kSlabsPerStage * kKBlockBytes, q_src + (int64_t)kb * kKBlockBytes, kKBlockBytes,
+            ptx::bulk_g2s(dst + kSlabsPerStage * kKBlockBytes, q_src + (int64_t)q_kb(kb) * kKBlockBytes, kKBlockBytes,
                           full_bar(st.idx));
         }
         __syncwarp();
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         }
         ptx::tc_fence_after();
         const uint32_t e_lo = st_base + (uint32_t)(st.idx * (kStageBytes >> 4));
-        const uint32_t q_lo = QRES ? q_base + (uint32_t)(kb * (kKBlockBytes >> 4))
+        const uint32_t q_lo = QRES ? q_base + (uint32_t)(q_kb(kb) * (kKBlockBytes >> 4))
                                    : e_lo + (uint32_t)(kSlabsPerStage * (kKBlockBytes >> 4));
         if (ptx::elect_one()) {
 #pragma unroll
@@ -588,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   }
 }
 
-inline int n_kblocks(const TileGeom& g) { return g.kblocks; }
+inline int n_kblocks(const TileGeom& g) { return g.kblocks; }  // slabs per row block in memory (split mode: both planes)
 inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
 inline int stage_bytes_for(const TileGeom& g, int cg) {
   return (kUnitBlocks / cg + (q_resident(g) ? 0 : 1)) * kKBlockBytes;
@@ -681,7 +688,13 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
   p.n_queries = a.n_queries;
   p.total_units = sc.total;
   p.nblk = (int)sc.nblk;
-  p.nkb = n_kblocks(a.g);
+  p.split_n = a.split_n;
+  p.nkb_q = n_kblocks(a.g);
+  p.nkb = a.split_n ? 3 * a.split_n : p.nkb_q;
+  if (a.split_n && p.nkb_q != 2 * a.split_n) {
+    set_error("tcgen05 search: split operands need 2 planes of %d K blocks, the geometry has %d", a.split_n, p.nkb_q);
+    return LK_ERR_INVALID;
+  }
   p.n_stages = n_stages_for(a.g, sc.cg);
   p.n_lists = a.n_lists;
   p.ksel = a.ksel;
@@ -705,7 +718,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     if (v >= 2 && v <= p.n_stages) p.n_stages = v;
   }
   const bool qres = q_resident(a.g);
-  const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb * kKBlockBytes : 0) +
+  const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb_q * kKBlockBytes : 0) +
                       (size_t)p.n_stages * stage_bytes_for(a.g, sc.cg);
   const int ksel = ksel_for(a.k);
   if (ksel != a.ksel) {

@@ -220,6 +220,63 @@ def test_simt_kernel_matches_oracle(lrb, n, b, dim, k, precision, metric, monkey
     _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
 
 
+FP32_TC_SHAPES = [
+    # n, b, dim, k          fp32 storage on the tensor cores: split-bf16 planes, K loop tripled
+    (1, 1, 64, 1),
+    (1000, 50, 32, 5),      # one K block per plane, K padding 32 -> 64
+    (5000, 257, 100, 7),    # K padding 100 -> 128: two K blocks per plane, resident query planes
+    (20000, 300, 384, 10),  # six K blocks per plane: the query planes are streamed with the stages
+    (3000, 40, 768, 100),
+    (60000, 1500, 64, 100),
+    (40000, 1, 384, 10),
+    (20000, 70, 256, 200),  # above one selector list: slab search over the planes
+]
+
+
+@pytest.mark.parametrize("n,b,dim,k", FP32_TC_SHAPES)
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_fp32_storage_on_tensor_cores_matches_oracle(lrb, n, b, dim, k, metric, monkeypatch):
+    """precision="fp32" through the tcgen05 kernel: rows and queries carried as two bf16 planes
+    (x = hi + lo, products hi*hi + hi*lo + lo*hi, fp32 accumulate) against the reference's fp32
+    arithmetic on the RAW fp32 inputs, at the north_star tolerance (1e-5 relative)."""
+    monkeypatch.setenv("LK_FORCE_KERNEL", "umma")
+    rng = np.random.default_rng(n * 3 + b)
+    emb = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((b, dim)).astype(np.float32))
+    if n >= 8 and b >= 4:
+        q[::4] = emb[(np.arange(0, b, 4) * 13) % n] + 0.05 * q[::4]
+    r = lrb.BruteForceRetriever(emb, [""] * n, None, metric=metric, precision="fp32")
+    d, i = r.search(q, k)
+    d_ref, i_ref = _oracle(emb, q, k, metric)
+    _assert_topk(d_ref, i_ref, d, i, l2=_l2(metric, emb, q))
+    # rows added later extend the planes; the exact FMA kernel on the same index agrees
+    if n >= 1000:
+        more = torch.from_numpy(rng.standard_normal((333, dim)).astype(np.float32))
+        r.index.add(more)
+        both = torch.cat([emb, more])
+        d2, i2 = r.index.search(q[:16], min(k, 128))
+        d_ref2, i_ref2 = _oracle(both, q[:16], min(k, 128), metric)
+        _assert_topk(d_ref2, i_ref2, d2, i2, l2=_l2(metric, both, q[:16]))
+        monkeypatch.setenv("LK_FORCE_KERNEL", "simt")
+        d3, i3 = r.index.search(q[:16], min(k, 128))
+        _assert_topk(d_ref2, i_ref2, d3, i3, l2=_l2(metric, both, q[:16]))
+
+
+def test_fp32_storage_picks_the_tensor_cores_for_sizeable_work(lrb):
+    """AUTO: config 1 at precision="fp32" (10k x 20k x 384) runs on the tcgen05 kernel -- the golden-vector
+    sized problems stay on the exact FMA kernel."""
+    rng = np.random.default_rng(9)
+    emb = torch.from_numpy(rng.standard_normal((20000, 384)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((2000, 384)).astype(np.float32))
+    r = lrb.BruteForceRetriever(emb, [""] * 20000, None, metric="cosine", precision="fp32")
+    r.index.set_timing(True)
+    d, i = r.search(q, 10)
+    kernel_ms = r.index.last_timing()[0]
+    d_ref, i_ref = _oracle(emb, q, 10, "cosine")
+    _assert_topk(d_ref, i_ref, d, i)
+    assert kernel_ms < 1.5, kernel_ms  # the fp32 FMA kernel needs ~2.8 ms for this batch
+
+
 @pytest.mark.parametrize("k", [6, 40, 128])
 @pytest.mark.parametrize("kernel", ["simt", "umma"])
 def test_ties_resolve_to_the_lowest_index(lrb, kernel, k, monkeypatch):
@@ -645,6 +702,50 @@ def test_ae_bf16_precision_matches_the_reference_fed_bf16_values(lrb, kind):
     assert ((z - ref32).abs() / ref32.abs().amax(dim=1, keepdim=True)).max().item() < 2e-2  # bf16-level vs fp32
     z32 = take(ae.set_precision("fp32").encode(x.cuda())).cpu()
     assert ((z32 - ref32).abs() / ref32.abs().amax(dim=1, keepdim=True)).max().item() < 3e-5
+
+
+@pytest.mark.parametrize("m", [1, 127, 129, 256, 385, 5000, 40_000, 300_001])
+def test_ae_pair_kernel_ragged_sizes(lrb, m, monkeypatch):
+    """The CTA-pair bf16 encoder (lk_ae_pair.cu): a lone row, odd numbers of 128-row tiles (the
+    peer CTA of the last pair has no tile), ragged last tiles, many tiles per cluster (every
+    barrier's parity wraps), host and device inputs -- against the reference's arithmetic fed
+    bf16-rounded operands, and against the single-CTA kernel computing the same thing."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    w = oracle.load_encoder_weights(np.load(os.path.join(gold, "ae_weights_cae.npz")), "cae")
+    rng = np.random.default_rng(m)
+    x = torch.from_numpy(rng.standard_normal((m, 384)).astype(np.float32))
+    x /= x.norm(dim=1, keepdim=True)
+    ae = lrb.load_autoencoder("cae", os.path.join(gold, "ae_weights_cae.npz")).set_precision("bf16")
+    n0 = lrb._native.launch_count()
+    z = ae.encode(x.cuda()).cpu()
+    assert lrb._native.launch_count() - n0 == -(-m // (1 << 18))  # one launch per step of 262,144 rows: no split pass
+    ref = oracle.ae_encode(x, w, "cae", precision="bf16")
+    err = (z - ref).abs() / ref.abs().amax(dim=1, keepdim=True)
+    assert err.max().item() < 2e-3 and (err > 2e-5).float().mean().item() < 0.02, (err.max().item(),)
+    assert torch.allclose(z.norm(dim=-1), torch.ones(m), atol=1e-6)
+    if m <= 5000:
+        np.testing.assert_array_equal(ae.encode(x).numpy(), z.numpy())  # host rows, staged by the library
+        monkeypatch.setenv("LK_AE_PAIR", "0")  # the single-CTA kernel on pre-split planes: same operands
+        z1 = ae.encode(x.cuda()).cpu()
+        e1 = (z - z1).abs() / ref.abs().amax(dim=1, keepdim=True)
+        assert e1.max().item() < 2e-3 and (e1 > 2e-5).float().mean().item() < 0.02
+
+
+@pytest.mark.parametrize("d_in,d_hidden,d_latent", [(64, 128, 16), (128, 256, 48), (384, 512, 64), (256, 1024, 33)])
+def test_ae_pair_kernel_other_dims(lrb, d_in, d_hidden, d_latent):
+    rng = np.random.default_rng(d_in + d_latent)
+    sd = {"encoder.0.weight": (rng.standard_normal((d_hidden, d_in)) / np.sqrt(d_in)).astype(np.float32),
+          "encoder.0.bias": (0.1 * rng.standard_normal(d_hidden)).astype(np.float32),
+          "encoder.2.weight": (rng.standard_normal((d_latent, d_hidden)) / np.sqrt(d_hidden)).astype(np.float32),
+          "encoder.2.bias": (0.1 * rng.standard_normal(d_latent)).astype(np.float32)}
+    ae = lrb.DenoisingAutoencoder(d_in, d_latent, d_hidden)
+    ae.load_state_dict(sd)
+    ae.set_precision("bf16")
+    x = torch.from_numpy(rng.standard_normal((1000, d_in)).astype(np.float32))
+    z = ae.encode(x.cuda()).cpu()
+    ref = oracle.ae_encode(x, oracle.load_encoder_weights(sd, "dae"), "dae", precision="bf16")
+    err = (z - ref).abs() / ref.abs().amax(dim=1, keepdim=True)
+    assert err.max().item() < 3e-3 and (err > 3e-5).float().mean().item() < 0.03, (err.max().item(),)
 
 
 def test_ae_tensor_core_kernel_is_rejected_for_unsupported_dims(lrb):

@@ -118,11 +118,19 @@ def test_ties_under_cta_pairs_and_rotation(lrb, b, k, metric):
     q = base[(torch.arange(b) * 37) % base_n].clone()
     d, i = r.search(q, k)
     first = ((torch.arange(b) * 37) % base_n).numpy()
-    for t in range(0, k - k % 3, 3):  # every triple of equal scores is in ascending row order
-        assert (d[:, t] == d[:, t + 1]).all() and (d[:, t] == d[:, t + 2]).all(), t
-        assert (i[:, t] < base_n).all() and (i[:, t] + base_n == i[:, t + 1]).all() and \
-            (i[:, t] + 2 * base_n == i[:, t + 2]).all(), t
-    np.testing.assert_array_equal(i[:, 0], first)
+    np.testing.assert_array_equal(i[:, :3], np.stack([first, first + base_n, first + 2 * base_n], 1))
+    # the engine's order is the total order (score desc, row asc) ...
+    assert (np.diff(d, axis=1) <= 0).all()
+    tie = d[:, 1:] == d[:, :-1]
+    assert (i[:, 1:][tie] > i[:, :-1][tie]).all()
+    # ... so a copy of a row can only be in the result if every lower-numbered copy is, with the same score
+    # (two DIFFERENT rows may tie exactly as well: a result row is not always a, a+n, a+2n, b, b+n, ...)
+    for row in range(b):
+        pos = {int(v): t for t, v in enumerate(i[row])}
+        for t, v in enumerate(i[row]):
+            if v >= base_n:
+                assert int(v) - base_n in pos and d[row, pos[int(v) - base_n]] == d[row, t], (row, t, int(v))
+    assert (tie.sum(axis=1) >= 2 * (k // 3)).all()  # every score comes (at least) three times
     _check(emb, q, k, metric, d, i)
 
 
@@ -132,7 +140,7 @@ def test_ties_under_cta_pairs_and_rotation(lrb, b, k, metric):
 # score = -(q-e)^T P (q-e), P = EmpiricalCovariance(E).precision (oracle.mahalanobis_search).
 # The reference has no Mahalanobis code: this pins OUR definition, not the reference's output.
 # ---------------------------------------------------------------------------------------
-MAHA_RECALL_FLOOR = {"bf16": 0.80, "fp32": 0.999}
+MAHA_RECALL_FLOOR = {"bf16": 0.97, "fp32": 0.999}
 
 
 def _aniso(n, d, seed, rot_seed=7):
