@@ -34,7 +34,9 @@
 //   acc0[2]      a0full (commit, multicast) -> epilogues -> a0empty (both CTAs' warps, on the leader)
 //   H            hfull / phfull (relay) -> layer-1 MMA -> hempty (commit, multicast)
 //   acc1         zfull (commit, multicast) -> Z epilogues -> zempty (on the leader)
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "lk_common.cuh"
 #include "lk_ptx.cuh"
@@ -48,13 +50,21 @@ constexpr int kPFirstEpi = 4, kPEpiWarps = 8;
 constexpr int kPFirstCvt = 12, kPCvtWarps = 8;
 constexpr int kPMaxStages = 8, kPMaxKb0 = 6;
 constexpr int kHalfSlab = kSlabBytes / 2;  // this CTA's 64 rows of a (hidden chunk, K block) slab of W0
+constexpr int kStageKb = 2;                // K blocks per W0 stage: one barrier wait and one commit per 8 MMAs (the
+                                           // issuing thread, not the tensor pipe, was the bottleneck at one K block)
+constexpr int kPStageBytes = kStageKb * kHalfSlab;
 constexpr int kPHeader = 1024;
 constexpr int kPTmemCols = 512, kPAcc1Col = 256;
+constexpr int kPXCol = 320;            // TMEM columns 320..511: the bf16 row tile, the A operand of layer 0 (32 per K block)
+constexpr int kXsRowBytes = 2 * 64 * kPMaxKb0 + 16;  // staging row: 768 bytes of bf16 + 16 of padding (conflict-free reads)
 constexpr int kPSmemBudget = 227 * 1024;
 
+// The barriers the leader's MMA warp waits on collect BOTH CTAs: the leader's own arrivals plus one from the
+// peer's relay warp (which waits for the same event on its own barrier first), so the issuing thread makes
+// one wait per event instead of two.
 enum PairBar {
-  B_FULL = 0, B_EMPTY = 8, B_PFULL = 16, B_XFULL = 24, B_PXFULL = 30, B_XEMPTY = 36, B_A0FULL = 42, B_A0EMPTY = 44,
-  B_HFULL = 46, B_PHFULL = 47, B_HEMPTY = 48, B_ZFULL = 49, B_ZEMPTY = 50, B_W1FULL = 51, B_PW1FULL = 52, B_COUNT = 53
+  B_FULL = 0, B_EMPTY = 8, B_XFULL = 16, B_XEMPTY = 22, B_A0FULL = 28, B_A0EMPTY = 30,
+  B_HFULL = 32, B_HEMPTY = 33, B_ZFULL = 34, B_ZEMPTY = 35, B_W1FULL = 36, B_COUNT = 37
 };
 
 enum PairErr { kPeProd = 401, kPeRelay = 402, kPeRelayX = 403, kPeRelayH = 404, kPeMmaA0 = 405, kPeMmaX = 406,
@@ -69,8 +79,9 @@ struct PairParams {
   const float* b1;
   float* z;                       // [m, n1_true]
   int64_t m;
-  int d_in, n_pair_tiles, nkb0, n_chunks, nkb1, n1, n1_true, l2norm, n_stages, z_vec;
+  int d_in, n_pair_tiles, nkb0, n_chunks, nkb1, n1, n1_true, l2norm, n_stages, z_vec, prefetch;
   int* err_flag;
+  long long* prof;  // bring-up (LK_AE_PROF): per cluster, cycles the MMA warp spent waiting per barrier kind + total
 };
 
 struct Ring {
@@ -99,6 +110,31 @@ __device__ __forceinline__ void ldg256_stream(const float* p, float (&v)[8]) {
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T on a CTA pair: the A operand (this CTA's 128 rows, K elements packed two per
+// 32-bit column) is read from tensor memory, so layer 0 spends its shared-memory bandwidth on the weights only
+// (with A in shared memory a 256 x 128 x 16 step reads 8 KB per 64 cycles: the whole 128 B/clk port)
+__device__ __forceinline__ void umma_bf16_2cta_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns, registers -> tensor memory (thread i writes lane base_lane + i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cvt_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 converter warps
+
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic stores -> tensor-core (async proxy) reads
 }
@@ -111,12 +147,12 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
   unsigned char* data = smem + kPHeader;
   data += (1024u - (ptx::smem_u32(data) & 1023u)) & 1023u;
   const int w1_half = (p.n1 / 2) * kRowBytes;  // this CTA's rows of one W1 K-block slab
-  unsigned char* x_sm = data;                                    // nkb0 slabs of 16 KB: the bf16 row tile
-  unsigned char* h_sm = x_sm + p.nkb0 * kSlabBytes;              // 2 slabs: one hidden chunk (128 units)
+  unsigned char* h_sm = data;                                    // 2 slabs: one hidden chunk (128 units)
   unsigned char* w1_sm = h_sm + 2 * kSlabBytes;                  // nkb1 half-slabs
-  unsigned char* stage_sm = w1_sm + p.nkb1 * w1_half;            // n_stages W0 half-slabs of 8 KB
-  float* b0_sm = reinterpret_cast<float*>(stage_sm + p.n_stages * kHalfSlab);  // n_chunks * 128 hidden biases
+  unsigned char* stage_sm = w1_sm + p.nkb1 * w1_half;            // n_stages stages of kStageKb W0 half-slabs
+  float* b0_sm = reinterpret_cast<float*>(stage_sm + p.n_stages * kPStageBytes);  // n_chunks * 128 hidden biases
   float* b1_sm = b0_sm + p.n_chunks * kBlockRows;                              // 64 latent biases (zero padded)
+  unsigned char* xs_sm = reinterpret_cast<unsigned char*>(b1_sm + 64);         // staging: the NEXT row tile in bf16, 128 padded rows
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -124,27 +160,24 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
   const int n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
 
   if (threadIdx.x == 0) {
+    const uint32_t relay = rank == 0 ? 1u : 0u;  // + the peer's relay on the leader's barriers
     for (int s = 0; s < kPMaxStages; ++s) {
-      ptx::mbar_init(bar(B_FULL + s), 1);
+      ptx::mbar_init(bar(B_FULL + s), 1 + relay);
       ptx::mbar_init(bar(B_EMPTY + s), 1);
-      ptx::mbar_init(bar(B_PFULL + s), 1);
     }
     for (int k = 0; k < kPMaxKb0; ++k) {
-      ptx::mbar_init(bar(B_XFULL + k), kPCvtWarps);
-      ptx::mbar_init(bar(B_PXFULL + k), 1);
+      ptx::mbar_init(bar(B_XFULL + k), kPCvtWarps + relay);
       ptx::mbar_init(bar(B_XEMPTY + k), 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar(B_A0FULL + a), 1);
       ptx::mbar_init(bar(B_A0EMPTY + a), 2 * kPEpiWarps);  // the leader's collects both CTAs' epilogue warps
     }
-    ptx::mbar_init(bar(B_HFULL), kPEpiWarps);
-    ptx::mbar_init(bar(B_PHFULL), 1);
+    ptx::mbar_init(bar(B_HFULL), kPEpiWarps + relay);
     ptx::mbar_init(bar(B_HEMPTY), 1);
     ptx::mbar_init(bar(B_ZFULL), 1);
     ptx::mbar_init(bar(B_ZEMPTY), kPEpiWarps);  // 4 Z warps per CTA, both CTAs
-    ptx::mbar_init(bar(B_W1FULL), 1);
-    ptx::mbar_init(bar(B_PW1FULL), 1);
+    ptx::mbar_init(bar(B_W1FULL), 1 + relay);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -179,12 +212,14 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters) {
       for (int c = 0; c < p.n_chunks && ok; ++c) {
         const unsigned char* wc = p.w0_slabs + (int64_t)c * 2 * p.nkb0 * kSlabBytes + rank * kHalfSlab;  // plane 0
-        for (int kb = 0; kb < p.nkb0; ++kb) {
+        for (int kb = 0; kb < p.nkb0; kb += kStageKb) {
+          const int nk = p.nkb0 - kb < kStageKb ? p.nkb0 - kb : kStageKb;
           if (!wait(bar(B_EMPTY + st.idx), st.phase ^ 1u)) { fail(kPeProd); ok = false; break; }
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar(B_FULL + st.idx), (uint32_t)kHalfSlab);
-            ptx::bulk_g2s(ptx::smem_u32(stage_sm + st.idx * kHalfSlab), wc + (int64_t)kb * kSlabBytes, kHalfSlab,
-                          bar(B_FULL + st.idx));
+            ptx::mbar_arrive_expect_tx(bar(B_FULL + st.idx), (uint32_t)(nk * kHalfSlab));
+            for (int j = 0; j < nk; ++j)
+              ptx::bulk_g2s(ptx::smem_u32(stage_sm + st.idx * kPStageBytes + j * kHalfSlab),
+                            wc + (int64_t)(kb + j) * kSlabBytes, kHalfSlab, bar(B_FULL + st.idx));
           }
           __syncwarp();
           st.advance(p.n_stages);
@@ -193,19 +228,25 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     }
   } else if (warp == 1 && rank != 0) {
     // ===================== peer relay: W0 stages and X slabs, in the order layer 0 consumes them =====
+    // (CTA-scope arrivals on the leader's barriers: they only order work that has already completed here --
+    // a landed bulk copy, shared-memory stores already fenced to the async proxy by their writers)
     Ring st;
     uint32_t t_local = 0;
     bool ok = true;
     for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters, ++t_local) {
       for (int c = 0; c < p.n_chunks && ok; ++c) {
-        for (int kb = 0; kb < p.nkb0; ++kb) {
+        for (int kb = 0; kb < p.nkb0 && ok; kb += kStageKb) {
+          const int nk = p.nkb0 - kb < kStageKb ? p.nkb0 - kb : kStageKb;
           if (c == 0) {
-            if (!wait(bar(B_XFULL + kb), t_local & 1u)) { fail(kPeRelayX); ok = false; break; }
-            if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_PXFULL + kb), 0);
-            __syncwarp();
+            for (int j = 0; j < nk; ++j) {
+              if (!wait(bar(B_XFULL + kb + j), t_local & 1u)) { fail(kPeRelayX); ok = false; break; }
+              if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_XFULL + kb + j), 0);
+              __syncwarp();
+            }
+            if (!ok) break;
           }
           if (!wait(bar(B_FULL + st.idx), st.phase)) { fail(kPeRelay); ok = false; break; }
-          if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_PFULL + st.idx), 0);
+          if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_FULL + st.idx), 0);
           __syncwarp();
           st.advance(p.n_stages);
         }
@@ -215,13 +256,13 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     // ===================== peer relay: W1 landed, hidden chunks ready =====================
     bool ok = wait(bar(B_W1FULL), 0u);
     if (!ok) fail(kPeRelayH);
-    if (ok && ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_PW1FULL), 0);
+    if (ok && ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_W1FULL), 0);
     __syncwarp();
     uint32_t g = 0;
     for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters) {
       for (int c = 0; c < p.n_chunks; ++c, ++g) {
         if (!wait(bar(B_HFULL), g & 1u)) { fail(kPeRelayH); ok = false; break; }
-        if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_PHFULL), 0);
+        if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_HFULL), 0);
         __syncwarp();
       }
     }
@@ -230,12 +271,24 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     const uint32_t idesc0 = ptx::idesc_bf16_f32(2 * kBlockRows, kBlockRows);  // M = 256 (pair), N = 128 hidden units
     const uint32_t idesc1 = ptx::idesc_bf16_f32(2 * kBlockRows, p.n1);        // N = latent columns
     const uint64_t desc_hi = ptx::smem_desc(0, 16, 1024);
-    const uint32_t x_lo = ptx::smem_u32(x_sm) >> 4, h_lo = ptx::smem_u32(h_sm) >> 4, w1_lo = ptx::smem_u32(w1_sm) >> 4,
-                   st_lo = ptx::smem_u32(stage_sm) >> 4;
-    auto desc = [&](uint32_t lo) { return desc_hi | (uint64_t)(lo & 0x3fffu); };
+    auto desc = [&](const void* sm) { return desc_hi | (uint64_t)((ptx::smem_u32(sm) >> 4) & 0x3fffu); };
+    // descriptors of the operand slabs; a K step of 16 elements is +32 bytes = +2 in the start-address field
+    // (no carry out of it: every operand lies below 256 KB)
+    const uint64_t h_desc = desc(h_sm), w1_desc = desc(w1_sm), st_desc = desc(stage_sm);
+    constexpr uint64_t kSlabStep = kSlabBytes >> 4, kHalfStep = kHalfSlab >> 4, kStageStep = kPStageBytes >> 4;
+    const uint64_t w1_step = (uint64_t)(w1_half >> 4);
     Ring st;
     uint32_t chunk_no = 0, l1_no = 0, t_local = 0;
     bool ok = true, w1_ready = false;
+    long long tw[6] = {0, 0, 0, 0, 0, 0};  // a0empty, xfull, full, hfull, zempty, w1full
+    const long long t_begin = clock64();
+    auto twait = [&](int kind, uint32_t b, uint32_t parity) -> bool {
+      if (p.prof == nullptr) return wait(b, parity) != 0;
+      const long long t0 = clock64();
+      const bool r = wait(b, parity) != 0;
+      tw[kind] += clock64() - t0;
+      return r;
+    };
     // layer 1 of a hidden chunk is issued AFTER layer 0 of the next chunk -- across row tiles too -- so that
     // the tensor pipe works on the next accumulator while the epilogue warps turn this one into H
     bool pend = false;       // a chunk whose layer 1 has not been issued yet
@@ -243,20 +296,19 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     uint32_t pend_tile = 0;
     auto layer1 = [&](int c, uint32_t tile_no) -> bool {
       if (!w1_ready) {
-        if (!wait(bar(B_W1FULL), 0u) || !wait(bar(B_PW1FULL), 0u)) { fail(kPeMmaW1); return false; }
+        if (!twait(5, bar(B_W1FULL), 0u)) { fail(kPeMmaW1); return false; }
         w1_ready = true;
       }
-      if (!wait(bar(B_HFULL), l1_no & 1u) || !wait(bar(B_PHFULL), l1_no & 1u)) { fail(kPeMmaH); return false; }
-      if (c == 0 && !wait(bar(B_ZEMPTY), (tile_no & 1u) ^ 1u)) { fail(kPeMmaZ); return false; }
+      if (!twait(3, bar(B_HFULL), l1_no & 1u)) { fail(kPeMmaH); return false; }
+      if (c == 0 && !twait(4, bar(B_ZEMPTY), (tile_no & 1u) ^ 1u)) { fail(kPeMmaZ); return false; }
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16_2cta(tmem_base + kPAcc1Col, desc(h_lo + (uint32_t)(j * (kSlabBytes >> 4)) + 2u * k),
-                                desc(w1_lo + (uint32_t)((2 * c + j) * (w1_half >> 4)) + 2u * k), idesc1,
-                                (c | j | k) != 0 ? 1u : 0u);
+            ptx::umma_bf16_2cta(tmem_base + kPAcc1Col, h_desc + j * kSlabStep + 2u * k,
+                                w1_desc + (uint64_t)(2 * c + j) * w1_step + 2u * k, idesc1, (c | j | k) != 0 ? 1u : 0u);
         ptx::umma_commit_2cta(bar(B_HEMPTY), 3);
         if (c == p.n_chunks - 1) ptx::umma_commit_2cta(bar(B_ZFULL), 3);
       }
@@ -268,26 +320,31 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
       for (int c = 0; c < p.n_chunks && ok; ++c) {
         // ---- layer 0 of hidden chunk c
         const uint32_t a = chunk_no & 1u;
-        if (!wait(bar(B_A0EMPTY + a), ((chunk_no >> 1) & 1u) ^ 1u)) { fail(kPeMmaA0); ok = false; break; }
-        for (int kb = 0; kb < p.nkb0; ++kb) {
-          if (c == 0) {  // the row tiles of both CTAs (the peer's through its relay)
-            if (!wait(bar(B_XFULL + kb), t_local & 1u) || !wait(bar(B_PXFULL + kb), t_local & 1u)) {
-              fail(kPeMmaX); ok = false; break;
-            }
+        if (!twait(0, bar(B_A0EMPTY + a), ((chunk_no >> 1) & 1u) ^ 1u)) { fail(kPeMmaA0); ok = false; break; }
+        for (int kb = 0; kb < p.nkb0 && ok; kb += kStageKb) {
+          const int nk = p.nkb0 - kb < kStageKb ? p.nkb0 - kb : kStageKb;
+          if (c == 0) {  // the row tiles of both CTAs
+            for (int j = 0; j < nk; ++j)
+              if (!twait(1, bar(B_XFULL + kb + j), t_local & 1u)) { fail(kPeMmaX); ok = false; }
+            if (!ok) break;
           }
-          if (!wait(bar(B_FULL + st.idx), st.phase) || !wait(bar(B_PFULL + st.idx), st.phase)) {
-            fail(kPeMmaFull); ok = false; break;
-          }
+          if (!twait(2, bar(B_FULL + st.idx), st.phase)) { fail(kPeMmaFull); ok = false; break; }
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            const uint32_t xa = x_lo + (uint32_t)(kb * (kSlabBytes >> 4));
-            const uint32_t wb = st_lo + (uint32_t)(st.idx * (kHalfSlab >> 4));
+            const uint32_t xa = tmem_base + kPXCol + (uint32_t)kb * 32u;  // 64 bf16 of a K block = 32 columns
+            const uint64_t wb = st_desc + (uint64_t)st.idx * kStageStep;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_2cta(tmem_base + a * kBlockRows, desc(xa + 2u * k), desc(wb + 2u * k), idesc0,
-                                  (kb | k) != 0 ? 1u : 0u);
+            for (int j = 0; j < kStageKb; ++j) {
+              if (j < nk) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_2cta_ts(tmem_base + a * kBlockRows, xa + (uint32_t)(j * 32 + k * 8), wb + j * kHalfStep + 2u * k,
+                                    idesc0, (kb | j | k) != 0 ? 1u : 0u);
+              }
+            }
             ptx::umma_commit_2cta(bar(B_EMPTY + st.idx), 3);
-            if (c == p.n_chunks - 1) ptx::umma_commit_2cta(bar(B_XEMPTY + kb), 3);  // slab kb: last reader done
+            if (c == p.n_chunks - 1)  // these slabs of X: last reader done
+              for (int j = 0; j < nk; ++j) ptx::umma_commit_2cta(bar(B_XEMPTY + kb + j), 3);
           }
           __syncwarp();
           st.advance(p.n_stages);
@@ -304,58 +361,81 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
       }
     }
     if (ok && pend) layer1(pend_c, pend_tile);
+    if (p.prof != nullptr && lane == 0) {
+      for (int i = 0; i < 6; ++i) p.prof[cid * 8 + i] = tw[i];
+      p.prof[cid * 8 + 6] = clock64() - t_begin;
+      p.prof[cid * 8 + 7] = t_local;
+    }
   } else if (warp >= kPFirstCvt) {
-    // ===================== converters: fp32 rows -> bf16 swizzled slabs =====================
-    // thread ct owns 16-byte chunk `piece` (8 columns) of rows (ct >> 3) + 32 j of every K block: a
-    // warp reads 4 rows x 256 contiguous bytes per load instruction and writes 512 contiguous bytes
-    // of the slab (conflict-free)
+    // ===================== converters: fp32 rows -> bf16 A operand in tensor memory =====================
+    // Phase A (a whole tile ahead of its use): thread ct owns the 8-column piece `piece` of rows
+    // (ct >> 3) + 32 j of every K block -- a warp reads 4 rows x 256 contiguous bytes per load instruction --
+    // rounds it to bf16 and parks it in the shared-memory staging tile.  Phase B (as the tensor core releases the
+    // K blocks of the tile before): thread = row (TMEM lane), two warps per lane quarter share a K block's 32
+    // columns: 64 staged bytes -> tcgen05.st.  The bar.sync pairs order staging reuse among the 8 warps; they are
+    // executed unconditionally (a timed-out wait only skips the work between them).
     const int ct = (int)threadIdx.x - kPFirstCvt * 32;
     const int piece = ct & 7, rbase = ct >> 3;
+    const int cw = warp - kPFirstCvt, quarter = cw & 3, hsel = cw >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t x_taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + kPXCol + (uint32_t)(hsel * 16);
     uint32_t t_local = 0;
     bool ok = true;
-    for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters, ++t_local) {
+    auto stage_tile = [&](int pt) {  // phase A
       const int64_t row0 = ((int64_t)pt * 2 + rank) * kBlockRows;
-      {  // this warp's 16 rows of the NEXT tile of this CTA go to L2 now: the loads below then pay L2 latency, not HBM's
-        const int64_t nrow0 = ((int64_t)(pt + n_clusters) * 2 + rank) * kBlockRows + (warp - kPFirstCvt) * (kBlockRows / kPCvtWarps);
-        if (pt + n_clusters < p.n_pair_tiles && nrow0 < p.m && lane == 0) {
-          const int64_t rows = p.m - nrow0 < kBlockRows / kPCvtWarps ? p.m - nrow0 : kBlockRows / kPCvtWarps;
-          prefetch_l2(p.x + nrow0 * p.d_in, (uint32_t)(rows * p.d_in * sizeof(float)));
-        }
-      }
-      float v[2][4][8];
-      auto load = [&](int kb, float (&dst)[4][8]) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int64_t grow = row0 + rbase + 32 * j;
-          if (grow < p.m) {
-            ldg256_stream(p.x + grow * p.d_in + kb * 64 + piece * 8, dst[j]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dst[j][e] = 0.f;
-          }
-        }
-      };
-      load(0, v[0]);
 #pragma unroll
       for (int kb = 0; kb < kPMaxKb0; ++kb) {
-        if (kb < p.nkb0 && ok) {
-          if (kb + 1 < p.nkb0) load(kb + 1, v[(kb + 1) & 1]);
-          if (!wait(bar(B_XEMPTY + kb), (t_local & 1u) ^ 1u)) { fail(kPeCvt); ok = false; }
-          if (ok) {
-            unsigned char* slab = x_sm + kb * kSlabBytes;
+        if (kb < p.nkb0) {
+          float v[4][8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float(&s)[8] = v[kb & 1][j];
-              const int r = rbase + 32 * j;
-              *reinterpret_cast<uint4*>(slab + slab_chunk_offset(r, piece)) =
-                  make_uint4(pack2(s[0], s[1]), pack2(s[2], s[3]), pack2(s[4], s[5]), pack2(s[6], s[7]));
+          for (int j = 0; j < 4; ++j) {
+            const int64_t grow = row0 + rbase + 32 * j;
+            if (grow < p.m) {
+              ldg256_stream(p.x + grow * p.d_in + kb * 64 + piece * 8, v[j]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j][e] = 0.f;
             }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar(B_XFULL + kb));
           }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(xs_sm + (rbase + 32 * j) * kXsRowBytes + kb * 128 + piece * 16) =
+                make_uint4(pack2(v[j][0], v[j][1]), pack2(v[j][2], v[j][3]), pack2(v[j][4], v[j][5]), pack2(v[j][6], v[j][7]));
         }
       }
+    };
+    if (cid < p.n_pair_tiles) stage_tile(cid);
+    cvt_bar_sync();
+    for (int pt = cid; pt < p.n_pair_tiles; pt += n_clusters, ++t_local) {
+      // phase B: staged tile -> tensor memory, K block by K block as the previous tile's readers finish
+      for (int kb = 0; kb < p.nkb0 && ok; ++kb) {
+        if (!wait(bar(B_XEMPTY + kb), (t_local & 1u) ^ 1u)) { fail(kPeCvt); ok = false; break; }
+        ptx::tc_fence_after();
+        uint32_t r[16];
+        const unsigned char* src = xs_sm + row * kXsRowBytes + kb * 128 + hsel * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 q4 = *reinterpret_cast<const uint4*>(src + j * 16);
+          r[4 * j] = q4.x; r[4 * j + 1] = q4.y; r[4 * j + 2] = q4.z; r[4 * j + 3] = q4.w;
+        }
+        tmem_st16(x_taddr + (uint32_t)kb * 32u, r);
+        tmem_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(B_XFULL + kb));
+      }
+      cvt_bar_sync();  // every warp has read its part of the staging tile
+      if (pt + n_clusters < p.n_pair_tiles && ok) {
+        {  // the tile after the next goes to L2 now (this warp's 16 rows of it)
+          const int64_t nrow0 = ((int64_t)(pt + 2 * n_clusters) * 2 + rank) * kBlockRows + cw * (kBlockRows / kPCvtWarps);
+          if (p.prefetch && pt + 2 * n_clusters < p.n_pair_tiles && nrow0 < p.m && lane == 0) {
+            const int64_t rows = p.m - nrow0 < kBlockRows / kPCvtWarps ? p.m - nrow0 : kBlockRows / kPCvtWarps;
+            prefetch_l2(p.x + nrow0 * p.d_in, (uint32_t)(rows * p.d_in * sizeof(float)));
+          }
+        }
+        stage_tile(pt + n_clusters);
+      }
+      cvt_bar_sync();  // the staging tile is complete
     }
   } else if (warp >= kPFirstEpi) {
     // ===================== epilogue =====================
@@ -476,9 +556,10 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
 }
 
 inline int pair_stages(int d_in, int d_hidden, int n1) {
-  const int fixed = kPHeader + 1024 + (d_in / 64) * kSlabBytes + 2 * kSlabBytes + (d_hidden / 64) * (n1 / 2) * kRowBytes +
-                    (d_hidden + 64) * (int)sizeof(float);
-  int s = (kPSmemBudget - fixed) / kHalfSlab;
+  (void)d_in;  // the row tile lives in tensor memory; its staging copy is sized for the widest supported row
+  const int fixed = kPHeader + 1024 + 2 * kSlabBytes + (d_hidden / 64) * (n1 / 2) * kRowBytes +
+                    (d_hidden + 64) * (int)sizeof(float) + kBlockRows * kXsRowBytes;
+  int s = (kPSmemBudget - fixed) / kPStageBytes;
   return s > kPMaxStages ? kPMaxStages : s;
 }
 
@@ -490,7 +571,7 @@ int ae_pair_supported(int d_in, int d_hidden, int d_latent, int sm_count) {
   if (d_in % 64 != 0 || d_in < 64 || d_in > 64 * kPMaxKb0 || d_hidden % 128 != 0 || d_hidden < 128 || d_latent < 1 ||
       d_latent > 64 || sm_count % 2 != 0)
     return 0;
-  return pair_stages(d_in, d_hidden, round_up(d_latent, 16)) >= 3;
+  return pair_stages(d_in, d_hidden, round_up(d_latent, 16)) >= 2;
 }
 
 int launch_ae_pair(const float* x, int64_t m, int d_in, int d_hidden, int d_latent, const unsigned char* w0_slabs,
@@ -518,11 +599,13 @@ int launch_ae_pair(const float* x, int64_t m, int d_in, int d_hidden, int d_late
     const int v = atoi(e);
     if (v >= 2 && v <= p.n_stages) p.n_stages = v;
   }
+  p.prefetch = 1;
+  if (const char* e = getenv("LK_AE_PF")) p.prefetch = atoi(e) != 0;  // bring-up: L2 prefetch of the next row tile
   p.z_vec = (d_latent == 64 && (reinterpret_cast<uintptr_t>(z) & 31u) == 0) ? 1 : 0;
   p.err_flag = err_flag;
-  const size_t smem = (size_t)kPHeader + 1024 + (size_t)p.nkb0 * kSlabBytes + 2 * kSlabBytes +
-                      (size_t)p.nkb1 * (p.n1 / 2) * kRowBytes + (size_t)p.n_stages * kHalfSlab +
-                      (size_t)(d_hidden + 64) * sizeof(float);
+  const size_t smem = (size_t)kPHeader + 1024 + 2 * kSlabBytes + (size_t)p.nkb1 * (p.n1 / 2) * kRowBytes +
+                      (size_t)p.n_stages * kPStageBytes + (size_t)(d_hidden + 64) * sizeof(float) +
+                      (size_t)kBlockRows * kXsRowBytes;
   LK_CUDA(cudaFuncSetAttribute(ae_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int clusters = p.n_pair_tiles < sm_count / 2 ? p.n_pair_tiles : sm_count / 2;
   cudaLaunchConfig_t cfg = {};
@@ -537,8 +620,26 @@ int launch_ae_pair(const float* x, int64_t m, int d_in, int d_hidden, int d_late
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  p.prof = nullptr;
+  const bool prof = getenv("LK_AE_PROF") != nullptr;  // bring-up: where the MMA warp waits (synchronises, prints to stderr)
+  if (prof) {
+    LK_CUDA(cudaMalloc((void**)&p.prof, (size_t)clusters * 8 * sizeof(long long)));
+    LK_CUDA(cudaMemsetAsync(p.prof, 0, (size_t)clusters * 8 * sizeof(long long), st));
+  }
   LK_CUDA(cudaLaunchKernelEx(&cfg, ae_pair_kernel, p));
   LK_CHECK_LAUNCH("ae_pair_kernel");
+  if (prof) {
+    std::vector<long long> h((size_t)clusters * 8);
+    LK_CUDA(cudaStreamSynchronize(st));
+    LK_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.prof);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < clusters; ++c)
+      for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)c * 8 + i] / clusters;
+    fprintf(stderr, "[ae_pair] m=%lld tiles/cluster=%.1f  MMA warp cycles: total %.0f  waits: a0empty %.0f  xfull %.0f  full %.0f  "
+            "hfull %.0f  zempty %.0f  w1full %.0f  (per tile: total %.0f)\n", (long long)m, a[7], a[6], a[0], a[1], a[2], a[3],
+            a[4], a[5], a[6] / (a[7] > 0 ? a[7] : 1));
+  }
   return LK_OK;
 }
 

@@ -608,7 +608,11 @@ inline int n_stages_for(const TileGeom& g, int cg) {
 // sorted register list / append buffer.  (Measured: the append buffer is slower than the register
 // list at k = 10 for every batch size, and 16 epilogue warps of 64 columns are slower than 8 of
 // 128 - spills at 96 registers, twice the lists; profiles/r01_microbench.log.)
-inline int ksel_for(int k) { return k <= 10 ? 10 : kBufCap; }
+inline int ksel_for(int k) {
+  if (const char* e = getenv("LK_KSEL_BUF"))  // bring-up override: the append-buffer selector for small k as well
+    if (atoi(e)) return kBufCap;
+  return k <= 10 ? 10 : kBufCap;
+}
 
 // CTA pairs (cta_group::2) once there are at least two query tiles to pair up; single CTAs for
 // the bandwidth-bound case of one query tile.
