@@ -166,17 +166,17 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
       ptx::mbar_init(bar(B_EMPTY + s), 1);
     }
     for (int k = 0; k < kPMaxKb0; ++k) {
-      ptx::mbar_init(bar(B_XFULL + k), kPCvtWarps + relay);
+      ptx::mbar_init(bar(B_XFULL + k), 2 * kPCvtWarps);   // both CTAs' converter warps, on the leader
       ptx::mbar_init(bar(B_XEMPTY + k), 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar(B_A0FULL + a), 1);
       ptx::mbar_init(bar(B_A0EMPTY + a), 2 * kPEpiWarps);  // the leader's collects both CTAs' epilogue warps
     }
-    ptx::mbar_init(bar(B_HFULL), kPEpiWarps + relay);
+    ptx::mbar_init(bar(B_HFULL), 2 * kPEpiWarps);          // both CTAs' epilogue warps, on the leader
     ptx::mbar_init(bar(B_HEMPTY), 1);
     ptx::mbar_init(bar(B_ZFULL), 1);
-    ptx::mbar_init(bar(B_ZEMPTY), kPEpiWarps);  // 4 Z warps per CTA, both CTAs
+    ptx::mbar_init(bar(B_ZEMPTY), 2 * kPEpiWarps);  // every epilogue warp of both CTAs
     ptx::mbar_init(bar(B_W1FULL), 1 + relay);
     ptx::fence_barrier_init();
   }
@@ -237,14 +237,6 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
       for (int c = 0; c < p.n_chunks && ok; ++c) {
         for (int kb = 0; kb < p.nkb0 && ok; kb += kStageKb) {
           const int nk = p.nkb0 - kb < kStageKb ? p.nkb0 - kb : kStageKb;
-          if (c == 0) {
-            for (int j = 0; j < nk; ++j) {
-              if (!wait(bar(B_XFULL + kb + j), t_local & 1u)) { fail(kPeRelayX); ok = false; break; }
-              if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_XFULL + kb + j), 0);
-              __syncwarp();
-            }
-            if (!ok) break;
-          }
           if (!wait(bar(B_FULL + st.idx), st.phase)) { fail(kPeRelay); ok = false; break; }
           if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_FULL + st.idx), 0);
           __syncwarp();
@@ -258,14 +250,6 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     if (!ok) fail(kPeRelayH);
     if (ok && ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_W1FULL), 0);
     __syncwarp();
-    uint32_t g = 0;
-    for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters) {
-      for (int c = 0; c < p.n_chunks; ++c, ++g) {
-        if (!wait(bar(B_HFULL), g & 1u)) { fail(kPeRelayH); ok = false; break; }
-        if (ptx::elect_one()) ptx::mbar_arrive_remote(bar(B_HFULL), 0);
-        __syncwarp();
-      }
-    }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader) =====================
     const uint32_t idesc0 = ptx::idesc_bf16_f32(2 * kBlockRows, kBlockRows);  // M = 256 (pair), N = 128 hidden units
@@ -422,7 +406,10 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
         tmem_wait_st();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(B_XFULL + kb));
+        if (lane == 0) {  // straight onto the leader's barrier (no relay hop)
+          if (rank != 0) ptx::mbar_arrive_remote(bar(B_XFULL + kb), 0);
+          else ptx::mbar_arrive(bar(B_XFULL + kb));
+        }
       }
       cvt_bar_sync();  // every warp has read its part of the staging tile
       if (pt + n_clusters < p.n_pair_tiles && ok) {
@@ -447,6 +434,68 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
     unsigned char* hrow = h_sm + ch * kSlabBytes + row * kRowBytes;
     uint32_t g = 0, t_local = 0;
     bool ok = true;
+    int z_pend_pt = -1;
+    uint32_t z_pend_tile = 0;
+    // Z row = acc1 + b1 (+ L2 normalisation): a thread owns one row and 32 of its 64 latent columns.  Run AFTER the first
+    // hidden chunk of the next tile has been handed to layer 1: the tensor pipe is busy with that tile's second
+    // chunk meanwhile, and layer 1 of the next tile only needs acc1 back after it
+    auto z_epilogue = [&](int z_pt, uint32_t z_tile) -> bool {
+      if (!wait(bar(B_ZFULL), z_tile & 1u)) { fail(kPeEpiZ); return false; }
+      ptx::tc_fence_after();
+      const int64_t grow = ((int64_t)z_pt * 2 + rank) * kBlockRows + row;
+      // this warp's 32 of the 64 latent columns (ch picks the half), one TMEM read, values kept in registers
+      float zv[32];
+      const bool have = ch * 32 < p.n1;
+      float ss = 0.f;
+      if (p.l2norm && (1 - ch) * 32 < p.n1) {  // the other half of the row: only its squares, for the L2 norm
+        uint32_t ro[32];
+        ptx::tmem_ld32(tmem_base + lane_addr + kPAcc1Col + (1 - ch) * 32, ro);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = (1 - ch) * 32 + j;
+          const float o = col < p.n1_true ? __uint_as_float(ro[j]) + b1_sm[col] : 0.f;
+          ss = fmaf(o, o, ss);
+        }
+      }
+      if (have) {  // this half: kept in registers until the store
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + lane_addr + kPAcc1Col + ch * 32, r);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          zv[j] = ch * 32 + j < p.n1_true ? __uint_as_float(r[j]) + b1_sm[ch * 32 + j] : 0.f;
+          ss = fmaf(zv[j], zv[j], ss);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zv[j] = 0.f;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {  // acc1 goes back to the (leader's) MMA warp as soon as it has been read
+        if (rank != 0) ptx::mbar_arrive_remote(bar(B_ZEMPTY), 0);
+        else ptx::mbar_arrive(bar(B_ZEMPTY));
+      }
+      const float scale = p.l2norm ? 1.0f / fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+      if (have && grow < p.m) {
+        float* out = p.z + grow * p.n1_true + ch * 32;
+        if (p.z_vec) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = zv[q8 * 8 + e] * scale;
+            ptx::stg256(out + q8 * 8, o);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ch * 32 + j < p.n1_true) out[j] = zv[j] * scale;
+        }
+      }
+      return true;
+    };
     for (int pt = cid; pt < p.n_pair_tiles && ok; pt += n_clusters, ++t_local) {
       for (int c = 0; c < p.n_chunks; ++c, ++g) {
         const uint32_t a = g & 1u;
@@ -454,21 +503,25 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
         ptx::tc_fence_after();
         const float* bias = b0_sm + c * kBlockRows + ch * 64;
         uint32_t hpk[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          ptx::tmem_ld32(tmem_base + lane_addr + a * kBlockRows + ch * 64 + half * 32, r);
+        {
+          uint32_t r0[32], r1[32];  // both halves in flight together
+          ptx::tmem_ld32(tmem_base + lane_addr + a * kBlockRows + ch * 64, r0);
+          ptx::tmem_ld32(tmem_base + lane_addr + a * kBlockRows + ch * 64 + 32, r1);
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {  // 8 hidden units at a time: two bias vectors, four packed words
-            const float4 ba = *reinterpret_cast<const float4*>(bias + half * 32 + q8 * 8);  // same address in every lane
-            const float4 bb = *reinterpret_cast<const float4*>(bias + half * 32 + q8 * 8 + 4);
-            const uint32_t* rr = r + q8 * 8;
-            uint32_t* o = hpk + half * 16 + q8 * 4;
-            o[0] = pack2(fmaxf(__uint_as_float(rr[0]) + ba.x, 0.f), fmaxf(__uint_as_float(rr[1]) + ba.y, 0.f));
-            o[1] = pack2(fmaxf(__uint_as_float(rr[2]) + ba.z, 0.f), fmaxf(__uint_as_float(rr[3]) + ba.w, 0.f));
-            o[2] = pack2(fmaxf(__uint_as_float(rr[4]) + bb.x, 0.f), fmaxf(__uint_as_float(rr[5]) + bb.y, 0.f));
-            o[3] = pack2(fmaxf(__uint_as_float(rr[6]) + bb.z, 0.f), fmaxf(__uint_as_float(rr[7]) + bb.w, 0.f));
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t* r = half == 0 ? r0 : r1;
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {  // 8 hidden units at a time: two bias vectors, four packed words
+              const float4 ba = *reinterpret_cast<const float4*>(bias + half * 32 + q8 * 8);  // same address in every lane
+              const float4 bb = *reinterpret_cast<const float4*>(bias + half * 32 + q8 * 8 + 4);
+              const uint32_t* rr = r + q8 * 8;
+              uint32_t* o = hpk + half * 16 + q8 * 4;
+              o[0] = pack2(fmaxf(__uint_as_float(rr[0]) + ba.x, 0.f), fmaxf(__uint_as_float(rr[1]) + ba.y, 0.f));
+              o[1] = pack2(fmaxf(__uint_as_float(rr[2]) + ba.z, 0.f), fmaxf(__uint_as_float(rr[3]) + ba.w, 0.f));
+              o[2] = pack2(fmaxf(__uint_as_float(rr[4]) + bb.x, 0.f), fmaxf(__uint_as_float(rr[5]) + bb.y, 0.f));
+              o[3] = pack2(fmaxf(__uint_as_float(rr[6]) + bb.z, 0.f), fmaxf(__uint_as_float(rr[7]) + bb.w, 0.f));
+            }
           }
         }
         ptx::tc_fence_before();
@@ -485,65 +538,20 @@ __global__ void __launch_bounds__(kPThreads, 1) ae_pair_kernel(const PairParams 
               make_uint4(hpk[4 * cj], hpk[4 * cj + 1], hpk[4 * cj + 2], hpk[4 * cj + 3]);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(B_HFULL));
+        if (lane == 0) {  // straight onto the leader's barrier (no relay hop)
+          if (rank != 0) ptx::mbar_arrive_remote(bar(B_HFULL), 0);
+          else ptx::mbar_arrive(bar(B_HFULL));
+        }
+        if (c == 0 && z_pend_pt >= 0) {  // the previous tile's latent rows
+          if (!z_epilogue(z_pend_pt, z_pend_tile)) { ok = false; break; }
+          z_pend_pt = -1;
+        }
       }
       if (!ok) break;
-      if (ch == 0) {  // ---- final: Z row = acc1 + b1 (+ L2 normalisation), one thread per row
-        if (!wait(bar(B_ZFULL), t_local & 1u)) { fail(kPeEpiZ); break; }
-        ptx::tc_fence_after();
-        const int64_t grow = ((int64_t)pt * 2 + rank) * kBlockRows + row;
-        float scale = 1.f;
-        if (p.l2norm) {
-          float ss = 0.f;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half * 32 < p.n1) {
-              uint32_t r[32];
-              ptx::tmem_ld32(tmem_base + lane_addr + kPAcc1Col + half * 32, r);
-              ptx::tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = half * 32 + j;
-                const float zv = col < p.n1_true ? __uint_as_float(r[j]) + b1_sm[col] : 0.f;
-                ss = fmaf(zv, zv, ss);
-              }
-            }
-          }
-          scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half * 32 < p.n1) {
-            uint32_t r[32];
-            ptx::tmem_ld32(tmem_base + lane_addr + kPAcc1Col + half * 32, r);
-            ptx::tmem_wait_ld();
-            if (grow < p.m) {
-              float* out = p.z + grow * p.n1_true + half * 32;
-              if (p.z_vec) {
-#pragma unroll
-                for (int q8 = 0; q8 < 4; ++q8) {
-                  float o[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    o[e] = (__uint_as_float(r[q8 * 8 + e]) + b1_sm[half * 32 + q8 * 8 + e]) * scale;
-                  ptx::stg256(out + q8 * 8, o);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (half * 32 + j < p.n1_true) out[j] = (__uint_as_float(r[j]) + b1_sm[half * 32 + j]) * scale;
-              }
-            }
-          }
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (rank != 0) ptx::mbar_arrive_remote(bar(B_ZEMPTY), 0);
-          else ptx::mbar_arrive(bar(B_ZEMPTY));
-        }
-      }
+      z_pend_pt = pt;
+      z_pend_tile = t_local;
     }
+    if (ok && z_pend_pt >= 0) z_epilogue(z_pend_pt, z_pend_tile);
   }
 
   // ===================== teardown =====================
