@@ -549,8 +549,11 @@ def cfg_c2(ctx: Ctx, sample, scale):
             z = zz
         tf, gbs = m * AE_FLOPS_PER_VEC / (ms * 1e-3) / 1e12, m * AE_BYTES_PER_VEC / (ms * 1e-3) / 1e9
         enc[prec] = {"vectors": m, "ms": ms, "vectors_per_s": m / (ms * 1e-3),
-                     "operands": "split-bf16 (hi + lo planes, 3 MMAs per product, fp32-level results)" if prec == "fp32"
-                     else "bf16 inputs / weights / hidden activations, fp32 accumulate (1 MMA per product)",
+                     "kernel": "split_rows_kernel + ae_umma_kernel" if prec == "fp32" else "ae_pair_kernel",
+                     "operands": "split-bf16 (hi + lo planes, 3 MMAs per product, fp32-level results: 3x the tensor work "
+                                 "by construction)" if prec == "fp32"
+                     else "bf16 inputs / weights / hidden activations, fp32 accumulate (1 MMA per product; north_star's "
+                          "stated precision); CTA pairs, fp32 rows converted in the kernel",
                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                   "frac": gbs / pk["hbm_gbs"], "tflops": tf,
                                   "tensor_frac_of_burst_peak": tf / pk["bf16_tflops"],
@@ -632,6 +635,25 @@ def cfg_c3(ctx: Ctx, sample, scale):
         rec["index_build_s"] = build_s
         out[f"c3_b{b}"] = rec
     index.close()
+    # the same corpus with fp32-stored whitened rows (split-bf16 planes on the tensor cores): what exactness costs
+    del case
+    torch.cuda.empty_cache()
+    index32 = lrb.ExactIndex(d, n, metric="mahalanobis", storage="fp32", device=dev.index,
+                             whiten=whitener_from_precision(prec))
+    for c in range(-(-n // CHUNK)):
+        index32.add(corpus_chunk(c, min(CHUNK, n - c * CHUNK), d, dev, unit=False, aniso=A))
+    case32 = SearchCase(ctx, index32, 0, "mahalanobis", 64)
+    q_host, qpos, planted = make_queries(64, d, n, dev, unit=False, aniso=A)
+    rec, res, _ = case32.measure(q_host, k, 6, 3, n, d)
+    rec["planted_neighbours_found"] = bool((res[1].cpu().numpy()[qpos, 0] == planted).all())
+    rec["workload"] = (f"mahalanobis top-{k}, 64 queries x {n} x {d}, fp32-stored whitened rows as split-bf16 planes "
+                       "(3 MMAs per product; 2x the bytes, 3x the flops of the bf16 rows)")
+    rec["roofline"]["bytes_per_launch"] = n * d * 4 + n * 4
+    rec["roofline"]["gbs_one_pass"] = rec["roofline"]["bytes_per_launch"] / (rec["kernel_ms"] * 1e-3) / 1e9
+    rec["roofline"]["achieved"] = rec["roofline"]["gbs_one_pass"]
+    rec["roofline"]["frac"] = rec["roofline"]["gbs_one_pass"] / ctx.pk["hbm_gbs"]
+    out["c3_b64_fp32"] = rec
+    index32.close()
     if sample is not None:  # Mahalanobis on the CPU = whitening + the reference's euclidean path
         emb = sample.view(d)
         for b in (1, 64):

@@ -51,7 +51,9 @@ constexpr int kKBlockBytes = kSlabBytes;                 // 16384
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarBytes = 512;                           // barriers, TMEM pointer, abort flag
-constexpr int kHeaderBytes = kBarBytes + kEpiWarps * 2 * kColsPerWarp * 4;  // + side rings
+constexpr int kStashStride = 9;                          // floats per lane: 8 scores of a column group + 1 of padding
+constexpr int kStashBytes = kEpiWarps * 32 * kStashStride * 4;
+constexpr int kHeaderBytes = kBarBytes + kEpiWarps * 2 * kColsPerWarp * 4 + kStashBytes;  // + side rings + score stash
 constexpr int kAlignSlack = 1024;                        // stages must be 1024-aligned (swizzle atom)
 constexpr uint32_t kLbo = 16;                            // unused by swizzled K-major layouts
 constexpr uint32_t kSbo = 8 * kRowBytes;                 // 1024: next 8-row group
@@ -377,6 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     const int ch = ew >> 2;                  // which half of the 128 columns
     const int lane_q = quarter * 32 + lane;  // query within the tile
     float* my_side = side_ring + ew * (2 * kColsPerWarp);
+    // this lane's 8 scores of a column group, for the lane-local insertions of crowded groups (below)
+    float* my_stash = side_ring + kEpiWarps * 2 * kColsPerWarp + (ew * 32 + lane) * kStashStride;
     Ring acc;
     int slot = 0;
     int qt = (int)(u0 / p.nblk) * CG + rank, b = (int)(u0 % p.nblk);
@@ -487,14 +491,39 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           }
         } else if (__any_sync(0xffffffffu, m > thr)) {
           // k <= 10: only the 8-column groups in which some lane has a hit are looked at again
+          unsigned pend = 0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (!__any_sync(0xffffffffu, mg[g] > thr)) continue;
-            unsigned pend = 0;
 #pragma unroll
             for (int j = 8 * g; j < 8 * g + 8; ++j)
               pend |= score(__uint_as_float(r[j]), sdc[j]) > thr ? (1u << j) : 0u;
-            unsigned umask = __reduce_or_sync(0xffffffffu, pend);
+          }
+          unsigned umask = __reduce_or_sync(0xffffffffu, pend);
+          if (__popc(umask) >= 4) {
+            // Crowded chunk (cold thresholds: the first rows of a segment, small corpora): serving the
+            // candidate columns one per turn makes the WHOLE warp run the insertion network once per column
+            // any lane hits.  Instead every lane parks the 8 scores of a group in shared memory and inserts
+            // its own hits, in row order: the warp pays for the lane with the most hits, not for the number
+            // of distinct columns.
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (!((umask >> (8 * g)) & 0xffu)) continue;  // warp-uniform
+#pragma unroll
+              for (int j = 0; j < 8; ++j) my_stash[j] = score(__uint_as_float(r[8 * g + j]), sdc[8 * g + j]);
+              unsigned mine = (pend >> (8 * g)) & 0xffu;
+              while (mine) {
+                const int jj = __ffs(mine) - 1;
+                mine &= mine - 1;
+                const float sc = my_stash[jj];
+                if (sc > thr) {  // rows in ascending order: strict '>' keeps the lower index
+                  top.insert(sc, row0 + chunk * 32 + 8 * g + jj);
+                  thr = top.threshold();
+                }
+              }
+              __syncwarp();
+            }
+          } else {
             while (umask) {  // warp-uniform: one candidate column per turn
               const int j = __ffs(umask) - 1;
               umask &= umask - 1;
