@@ -173,7 +173,9 @@ int lk_rank_positive(int device, const float* queries, const float* docs, int64_
  *      host-side process group).  lk_comm_exchange_merge is ONE kernel per rank and call:
  *      it stores this rank's b x k candidates (global ids) straight into every peer's buffer
  *      over NVLink, releases per-query flags, waits for the peers' flags and merges the
- *      world x k candidates of each query.  All ranks must call it in the same order.  The wait for
+ *      world x k candidates of each query.  All ranks must call it in the same order.  Every rank's k
+ *      candidates of a query must be sorted best first under (score desc, id asc), as lk_index_search
+ *      returns them (short lists padded at the end with id -1): the merge ranks them by binary searches.  The wait for
  *      a peer is bounded (60 s; LK_XCHG_TIMEOUT_S overrides) only to turn a dead peer into an error:
  *      on a timeout the affected queries come back as id -1 / score -inf and lk_comm_check reports
  *      LK_ERR_CUDA -- callers that keep the outputs on the device must call lk_comm_check.

@@ -967,6 +967,11 @@ def test_peer_exchange_protocol_on_one_gpu(lrb, world, b, k):
         ci[:, -1, -3:] = -1  # a short shard pads with -1 / -inf
         cd[:, -1, -3:] = -np.inf
         cd[0, 0, 0] = cd[0, 1 % world, 0]  # a tie across ranks
+        if rep == 2:  # massive ties within and across the lists
+            cd = np.where(np.isfinite(cd), np.round(cd, 1), cd).astype(np.float32)
+        # every rank's list sorted by (score desc, id asc) like a search result: the merge ranks by binary searches
+        order = np.lexsort((np.where(ci < 0, np.iinfo(np.int64).max, ci), -cd), axis=2)
+        cd, ci = np.take_along_axis(cd, order, 2), np.take_along_axis(ci, order, 2)
         for r, c in enumerate(comms):
             c.begin()
             c.publish(torch.from_numpy(cd[:, r]).cuda(), torch.from_numpy(ci[:, r]).cuda())
