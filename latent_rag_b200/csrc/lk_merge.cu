@@ -110,23 +110,34 @@ __global__ void __launch_bounds__(kSelThreads) merge_select_kernel(const float* 
   const IdxT* ci = pi + q * n_lists * list_stride;
   const int* cc = pc ? pc + q * n_lists : nullptr;
   // f(key, slot offset, is_candidate) for every filled slot, warp-converged (one list per warp turn)
+  // (four 32-entry strides per turn: the 8 loads of a lane are in flight together -- with one stride per turn a
+  // warp paid one L2 round trip per 32 candidates, ~40 in a row for 38 k candidates of a single query)
   auto for_each_slot = [&](auto&& f) {
     for (int l = warp; l < n_lists; l += kSelThreads / 32) {
       int n = list_len;
       if (cc) n = min(n, __ldcg(cc + l));
       const int64_t base = (int64_t)l * list_stride;
-      for (int e0 = 0; e0 < n; e0 += 32) {
-        const int e = e0 + lane;
-        uint32_t key = 0u;
-        bool ok = false;
-        if (e < n) {
-          key = order_key(__ldcg(cs + base + e));
-          if (key > kKeyNegInf && key <= kKeyPosInf) {
-            const IdxT id = __ldcg(ci + base + e);
-            ok = id >= 0 && id != IdxTraits<IdxT>::sentinel();
-          }
+      for (int e0 = 0; e0 < n; e0 += 128) {
+        float sv[4];
+        IdxT iv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + 32 * u + lane;
+          sv[u] = e < n ? __ldcg(cs + base + e) : 0.f;
+          iv[u] = e < n ? __ldcg(ci + base + e) : (IdxT)-1;
         }
-        f(key, base + e, ok);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e0 + 32 * u >= n) break;  // warp-uniform
+          const int e = e0 + 32 * u + lane;
+          uint32_t key = 0u;
+          bool ok = false;
+          if (e < n) {
+            key = order_key(sv[u]);
+            ok = key > kKeyNegInf && key <= kKeyPosInf && iv[u] >= 0 && iv[u] != IdxTraits<IdxT>::sentinel();
+          }
+          f(key, base + e, ok);
+        }
       }
     }
   };
