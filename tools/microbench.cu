@@ -120,6 +120,64 @@ __global__ void __launch_bounds__(128) mma_rate(int n_cols, int layout, int iter
   }
 }
 
+
+// ---- 2b. MMA rate on a CTA pair (cta_group::2, M = 256): N = 64 / 128 / 256, A operand in shared or tensor memory.
+//          The leader issues `iters` groups of 4 MMAs back to back on static (zero) operands; one multicast commit.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) mma_rate_pair(int n_cols, int a_in_tmem, int iters,
+                                                                                  long long* cycles, int* err) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm + 64);
+  unsigned char* a_sm = sm + 1024;             // 16 KB: this CTA's 128 rows of A
+  unsigned char* b_sm = a_sm + 16384;          // 16 KB: this CTA's half of B (up to 128 of N = 256 rows)
+  for (int i = threadIdx.x; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(a_sm)[i] = 0;
+  const uint32_t bar = ptx::smem_u32(bars);
+  const uint32_t rank = ptx::cluster_ctarank();
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) {
+    ptx::tmem_alloc2(ptx::smem_u32(tmem_ptr), 512);
+    ptx::tmem_relinquish2();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = ptx::idesc_bf16_f32(256, n_cols);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem + (uint32_t)((it & 1) * 128);  // accumulators in columns 0..255, A (if in TMEM) in 320..
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t db = ptx::smem_desc(ptx::smem_u32(b_sm) + k * 32, 16, 1024, 2);
+        if (a_in_tmem) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(tmem + 320u + 8u * k),
+                       "l"(db), "r"(idesc), "r"((uint32_t)(k != 0))
+                       : "memory");
+        } else {
+          ptx::umma_bf16_2cta(d, ptx::smem_desc(ptx::smem_u32(a_sm) + k * 32, 16, 1024, 2), db, idesc, k != 0);
+        }
+      }
+    }
+    ptx::umma_commit_2cta(bar, 3);
+    if (!ptx::mbar_wait(bar, 0)) atomicExch(err, 4);
+    if (blockIdx.x == 0) cycles[0] = clock64() - t0;
+  } else if (threadIdx.x == 0) {
+    if (!ptx::mbar_wait(bar, 0)) atomicExch(err, 5);
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();
+  if (threadIdx.x < 32) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem, 512);
+  }
+}
+
 // ---- 4. TMEM read rate: tcgen05.ld.32x32b.x32 from n_warps warps, `depth` loads in flight per warp
 __global__ void __launch_bounds__(512) tmem_read_rate(int n_warps, int depth, int iters, long long* cycles, float* sink) {
   __shared__ uint32_t tmem_ptr;
@@ -238,6 +296,28 @@ int main() {
                (double)h / (iters * 4), herr);
       }
     }
+  }
+  {
+    long long* cyc;
+    int* err2;
+    CK(cudaMalloc(&cyc, 8));
+    CK(cudaMalloc(&err2, 4));
+    CK(cudaMemset(err2, 0, 4));
+    CK(cudaFuncSetAttribute(mma_rate_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 32768));
+    for (int a_in_tmem : {0, 1})
+      for (int n : {64, 128, 256}) {
+        const int iters = 2000;
+        for (int rep = 0; rep < 2; ++rep) {
+          mma_rate_pair<<<sms / 2 * 2, 128, 1024 + 32768>>>(n, a_in_tmem, iters, cyc, err2);
+          CK(cudaDeviceSynchronize());
+        }
+        long long h = 0;
+        int herr = 0;
+        CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&herr, err2, 4, cudaMemcpyDeviceToHost));
+        printf("tcgen05.mma cta_group::2 M=256 N=%3d A in %s: %.1f cycles per MMA (K=16), err=%d\n", n,
+               a_in_tmem ? "TMEM" : "smem", (double)h / (iters * 4), herr);
+      }
   }
   {
     long long* cyc;
