@@ -28,6 +28,10 @@ class BruteForceRetriever(BatchedRetrieveMixin):
       device           CUDA device index (default: torch's current device)
       precision_matrix [D, D] inverse covariance for mahalanobis (default: estimated from
                        `embeddings` like sklearn's EmpiricalCovariance)
+      keep_source      keep a REFERENCE (not a copy) to `embeddings` so that the reference's public
+                       `.emb` attribute can be rebuilt on demand (default True: drop-in).  False lets
+                       the caller's corpus tensor be freed -- the engine's own copy lives in HBM --
+                       and makes `.emb` raise.
     """
 
     def __init__(
@@ -40,6 +44,7 @@ class BruteForceRetriever(BatchedRetrieveMixin):
         precision: str = "bf16",
         device: Optional[int] = None,
         precision_matrix: Optional[np.ndarray] = None,
+        keep_source: bool = True,
     ):
         if doc_ids is not None:
             assert len(texts) == len(doc_ids), "len mismatch (texts vs doc_ids)"  # bruteforce.py:33-34
@@ -51,7 +56,7 @@ class BruteForceRetriever(BatchedRetrieveMixin):
         self.metric = metric
         self.precision = precision
         self._stats = StatsTracker()
-        self._src = embeddings  # a reference, not a copy: only `.emb` ever reads it again
+        self._src = embeddings if keep_source else None  # a reference, not a copy: only `.emb` ever reads it again
 
         if isinstance(embeddings, np.ndarray):
             embeddings = torch.from_numpy(embeddings)
@@ -78,6 +83,8 @@ class BruteForceRetriever(BatchedRetrieveMixin):
     # the engine's copy lives in HBM as bf16 tiles, so this one is rebuilt on demand
     @property
     def emb(self) -> torch.Tensor:
+        if self._src is None:
+            raise AttributeError("this retriever was built with keep_source=False: the corpus only exists as tiles in HBM")
         e = self._src if torch.is_tensor(self._src) else torch.from_numpy(np.asarray(self._src))
         e = e.detach().to("cpu", torch.float32)
         return F.normalize(e, p=2, dim=1).contiguous() if self.metric == "cosine" else e.contiguous()
