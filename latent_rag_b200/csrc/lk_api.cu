@@ -80,7 +80,7 @@ struct lk_index {
   const unsigned char* sv_tiles = nullptr;
   TileGeom sv_g;
   int sv_split = 0;
-  Buf stage, white, q_tiles, q_side, q_planes, part_s, part_i, part_c, out_s, out_i, debug;
+  Buf stage, white, q_tiles, q_side, q_planes, part_s, part_i, part_c, out_s, out_i, debug, mtmp_s, mtmp_i;
   Buf deep_s, deep_i, deep_last, deep_flags, deep_tiles, deep_side;  // slab search (k > 128)
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -127,7 +127,7 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->ticket) cudaFree(ix->ticket);
   if (ix->pin) cudaFreeHost(ix->pin);
   if (ix->planes) cudaFree(ix->planes);
-  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->q_planes, &ix->part_s, &ix->part_i, &ix->part_c,
+  Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->q_planes, &ix->mtmp_s, &ix->mtmp_i, &ix->part_s, &ix->part_i, &ix->part_c,
                  &ix->out_s, &ix->out_i, &ix->debug, &ix->deep_s, &ix->deep_i, &ix->deep_last, &ix->deep_flags,
                  &ix->deep_tiles, &ix->deep_side};
   for (Buf* b : bufs) b->release();
@@ -483,12 +483,23 @@ static int search_rows(lk_index* ix, int which, SearchArgs a, int64_t idx_base, 
     a.part_cnt = a0.part_cnt = ix->part_c.as<int>();
   }
 
+  // scratch of the two-level merge (a few queries, very many candidates each)
+  constexpr int64_t kMergeTmpEntries = 148 * kMaxK;
+  float* mt_s = nullptr;
+  int64_t* mt_i = nullptr;
+  if (b * 2 <= 148) {
+    if ((rc = ix->mtmp_s.ensure(kMergeTmpEntries * sizeof(float))) != LK_OK) return rc;
+    if ((rc = ix->mtmp_i.ensure(kMergeTmpEntries * sizeof(int64_t))) != LK_OK) return rc;
+    mt_s = ix->mtmp_s.as<float>();
+    mt_i = ix->mtmp_i.as<int64_t>();
+  }
+
   // fused distance + selection
   if (events) LK_CUDA(cudaEventRecord(ix->ev[1], st));
   if (seed_rows > 0) {  // (the tcgen05 kernel marks the list slots it does not own itself)
     if ((rc = launch_search_umma(a0, ix->sm_count, st)) != LK_OK) return rc;
     rc = launch_merge_i32(a0.part_scores, a0.part_idx, a0.part_cnt, b, a0.n_lists, merge_len, a0.ksel, k, 0, d_s,
-                          d_i, st);
+                          d_i, st, mt_s, mt_i, kMergeTmpEntries);
     if (rc != LK_OK) return rc;
     a.seed = d_s;  // read at the start of the main kernel's segments, overwritten by the final merge
   }
@@ -521,7 +532,7 @@ static int search_rows(lk_index* ix, int which, SearchArgs a, int64_t idx_base, 
   // append-buffer selector (ksel > kMaxK) leaves an unordered superset of its best k anywhere
   // in the slot
   return launch_merge_i32(a.part_scores, a.part_idx, a.part_cnt, b, a.n_lists, merge_len, a.ksel, k, idx_base, d_s,
-                          d_i, st);
+                          d_i, st, mt_s, mt_i, kMergeTmpEntries);
 }
 
 // ------------------------------------------------------------------------------------

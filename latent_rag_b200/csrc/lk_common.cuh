@@ -140,8 +140,10 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st);
 
 // merge [b, n_lists, list_len] candidates -> [b, k]; idx type int32 (+base) or int64
 // pc: optional [b, n_lists] fill counts of the lists (entries past the count are not read)
+// tmp_s / tmp_i (optional, tmp_entries each): scratch for the two-level merge of a few queries with very many candidates
 int launch_merge_i32(const float* ps, const int32_t* pi, const int* pc, int64_t b, int n_lists, int list_len,
-                     int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st);
+                     int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st,
+                     float* tmp_s = nullptr, int64_t* tmp_i = nullptr, int64_t tmp_entries = 0);
 int launch_merge_i64(const float* ps, const int64_t* pi, int64_t b, int n_lists, int list_len, int k,
                      float* out_s, int64_t* out_i, cudaStream_t st);
 

@@ -292,9 +292,64 @@ __global__ void __launch_bounds__(kSelThreads) merge_select_kernel(const float* 
   }
 }
 
+
+// Merge of P SORTED lists of k entries per query (the second level of the two-level selection below; every list is
+// sorted under the total order (score desc, id asc), unfilled slots (id < 0) at its end): by RANKING -- the final
+// position of entry j of list r is j + the number of better entries in each other list, one binary search per other
+// list, all threads of the CTA.  P * k <= 2048.
+constexpr int kSortedMaxCand = 2048;
+__global__ void __launch_bounds__(256) merge_sorted_kernel(const float* __restrict__ ps, const int64_t* __restrict__ pi,
+                                                           int parts, int k, float* __restrict__ out_s,
+                                                           int64_t* __restrict__ out_i) {
+  __shared__ float cs[kSortedMaxCand];
+  __shared__ int64_t ci[kSortedMaxCand];
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  const int n = parts * k;
+  for (int e = tid; e < n; e += 256) {
+    float v = __ldcg(ps + q * n + e);
+    int64_t id = __ldcg(pi + q * n + e);
+    if (id < 0 || !(v == v)) {
+      v = -INFINITY;
+      id = INT64_MAX;
+    }
+    cs[e] = v;
+    ci[e] = id;
+  }
+  for (int j = tid; j < k; j += 256) {
+    out_s[q * k + j] = -INFINITY;
+    out_i[q * k + j] = -1;
+  }
+  __syncthreads();
+  for (int e = tid; e < n; e += 256) {
+    const int r = e / k, j = e - r * k;
+    const float v = cs[e];
+    const int64_t id = ci[e];
+    if (id == INT64_MAX) continue;
+    int pos = j;
+    for (int r2 = 0; r2 < parts && pos < k; ++r2) {
+      if (r2 == r) continue;
+      const float* l2s = cs + r2 * k;
+      const int64_t* l2i = ci + r2 * k;
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (better(l2s[mid], l2i[mid], v, id)) lo = mid + 1;
+        else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < k) {
+      out_s[q * k + pos] = v;
+      out_i[q * k + pos] = id;
+    }
+  }
+}
+
 template <typename IdxT>
 int launch_merge(const float* ps, const IdxT* pi, const int* pc, int64_t b, int n_lists, int list_len,
-                 int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st) {
+                 int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st,
+                 float* tmp_s = nullptr, int64_t* tmp_i = nullptr, int64_t tmp_entries = 0) {
   if (b <= 0) return LK_OK;
   if (k < 1 || k > kMaxK) {
     set_error("merge: k=%d outside 1..%d", k, kMaxK);
@@ -308,6 +363,32 @@ int launch_merge(const float* ps, const IdxT* pi, const int* pc, int64_t b, int 
   const char* force = getenv("LK_MERGE");  // bring-up: "insert" / "select"
   bool select = b <= 1024 && n_cand >= 2048;
   if (force) select = !strcmp(force, "select");
+  // A few queries with tens of thousands of candidates each (one query over the 296 append buffers of a top-100
+  // search): one CTA per query leaves the GPU empty and takes ~100 us.  Two levels instead: the lists of a query
+  // are cut into P contiguous parts, P CTAs select each part's top-k (the same kernel on b * P pseudo-queries:
+  // the list arrays are contiguous per query, so part p of query q is pseudo-query q * P + p), and a second,
+  // small merge folds the P sorted lists.
+  if (select && tmp_s != nullptr && tmp_i != nullptr && n_cand >= 16384 && b * 2 <= 148) {
+    int parts = 0;
+    for (int cand = 16; cand >= 2; cand >>= 1)
+      if (n_lists % cand == 0 && b * cand <= 148 && (int64_t)(n_lists / cand) * list_len >= 2048 &&
+          b * cand * (int64_t)k <= tmp_entries) {
+        parts = cand;
+        break;
+      }
+    if (parts > 1) {
+      const int64_t n_part_cand = (int64_t)(n_lists / parts) * list_len;
+      const int key_cap = (int)(n_part_cand < kSelMaxKeys ? n_part_cand : kSelMaxKeys);
+      LK_CUDA(cudaFuncSetAttribute(merge_select_kernel<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kSelMaxKeys * sizeof(uint32_t))));
+      merge_select_kernel<IdxT><<<(unsigned)(b * parts), kSelThreads, (size_t)key_cap * sizeof(uint32_t), st>>>(
+          ps, pi, pc, b * parts, n_lists / parts, list_len, list_stride, k, idx_base, key_cap, tmp_s, tmp_i);
+      LK_CHECK_LAUNCH("merge_select_kernel");
+      merge_sorted_kernel<<<(unsigned)b, 256, 0, st>>>(tmp_s, tmp_i, parts, k, out_s, out_i);
+      LK_CHECK_LAUNCH("merge_sorted_kernel");
+      return LK_OK;
+    }
+  }
   if (select) {
     const int key_cap = (int)(n_cand < kSelMaxKeys ? n_cand : kSelMaxKeys);
     const size_t smem = (size_t)key_cap * sizeof(uint32_t);
@@ -330,8 +411,10 @@ int launch_merge(const float* ps, const IdxT* pi, const int* pc, int64_t b, int 
 }  // namespace
 
 int launch_merge_i32(const float* ps, const int32_t* pi, const int* pc, int64_t b, int n_lists, int list_len,
-                     int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st) {
-  return launch_merge<int32_t>(ps, pi, pc, b, n_lists, list_len, list_stride, k, idx_base, out_s, out_i, st);
+                     int list_stride, int k, int64_t idx_base, float* out_s, int64_t* out_i, cudaStream_t st,
+                     float* tmp_s, int64_t* tmp_i, int64_t tmp_entries) {
+  return launch_merge<int32_t>(ps, pi, pc, b, n_lists, list_len, list_stride, k, idx_base, out_s, out_i, st, tmp_s,
+                               tmp_i, tmp_entries);
 }
 
 int launch_merge_i64(const float* ps, const int64_t* pi, int64_t b, int n_lists, int list_len, int k,

@@ -133,6 +133,34 @@ __global__ void __launch_bounds__(128) whiten_kernel(const InT* __restrict__ row
   }
 }
 
+// The same product for a FEW rows (a query batch): the kernel above gives all dim columns of 8 rows to one CTA of
+// 128 threads -- 9216 dependent fp64 FMAs per thread and the whole L (1.2 MB at dim 384) through one SM, ~150 us
+// for a single query.  Here a CTA takes 8 rows x 32 columns (thread = column x row pair), so one query spreads
+// over dim / 32 CTAs and finishes in a few microseconds.
+template <typename InT>
+__global__ void __launch_bounds__(128) whiten_few_kernel(const InT* __restrict__ rows, int64_t n, int dim,
+                                                         const double* __restrict__ L, float* __restrict__ out) {
+  extern __shared__ double xs[];  // [8][dim]
+  const int64_t r0 = (int64_t)blockIdx.x * 8;
+  const int nr = (int)min((int64_t)8, n - r0);
+  for (int i = threadIdx.x; i < 8 * dim; i += blockDim.x) {
+    const int rr = i / dim, c = i - rr * dim;
+    xs[i] = rr < nr ? (double)load_as_float<InT>(rows + (r0 + rr) * dim + c) : 0.0;
+  }
+  __syncthreads();
+  const int j = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int ra = (threadIdx.x >> 5) * 2;  // this thread's two rows
+  if (j >= dim) return;
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = 0; i < dim; ++i) {  // same summation order as whiten_kernel: bit-identical results
+    const double l = L[(int64_t)i * dim + j];
+    a0 = fma(xs[ra * dim + i], l, a0);
+    a1 = fma(xs[(ra + 1) * dim + i], l, a1);
+  }
+  if (ra < nr) out[(r0 + ra) * dim + j] = (float)a0;
+  if (ra + 1 < nr) out[(r0 + ra + 1) * dim + j] = (float)a1;
+}
+
 }  // namespace
 
 int launch_tile_rows(const void* rows, int rows_dtype, int64_t n, const TileGeom& g, void* tiles,
@@ -177,6 +205,16 @@ int launch_whiten(const void* rows, int rows_dtype, int64_t n, int dim, const do
   if (smem > 48 * 1024) {
     set_error("whitening supports dim <= 768 (got %d)", dim);
     return LK_ERR_UNSUPPORTED;
+  }
+  if (n <= 4096) {  // a query batch: spread the columns over CTAs as well
+    const dim3 g2(grid, (unsigned)((dim + 31) / 32));
+    if (rows_dtype == LK_F32)
+      whiten_few_kernel<float><<<g2, 128, smem, st>>>(static_cast<const float*>(rows), n, dim, L, out);
+    else
+      whiten_few_kernel<__nv_bfloat16>
+          <<<g2, 128, smem, st>>>(static_cast<const __nv_bfloat16*>(rows), n, dim, L, out);
+    LK_CHECK_LAUNCH("whiten_few_kernel");
+    return LK_OK;
   }
   if (rows_dtype == LK_F32)
     whiten_kernel<float><<<grid, 128, smem, st>>>(static_cast<const float*>(rows), n, dim, L, out);
