@@ -4,8 +4,9 @@ Follows `retrieval/bruteforce.py:26-83` and `retrieval/common.py:18-32` of the
 reference (paths relative to /root/reference).  torch CPU ops are used on purpose:
 the reference *is* `F.normalize` + `mm` + `torch.topk` on CPU, so the same ATen
 calls reproduce it bit for bit.  The only structural change is that queries are
-processed in row chunks so the `[B, N]` score matrix stays bounded; every row's
-result is independent of the chunking.
+processed in row chunks so the `[B, N]` score matrix stays bounded; a row's neighbours
+do not depend on the chunking (its scores can move in the last bit: ATen picks different
+GEMM kernels for different batch heights, exactly as the reference's own `q @ emb.T` does).
 """
 from __future__ import annotations
 

@@ -191,3 +191,19 @@ def test_sbert_oracle_matches_transformers_outputs(golden, name, n, s):
     emb = oracle.sbert_encode(w, cfg, ids, mask).numpy()
     np.testing.assert_allclose(emb, g[f"{name}_emb"], atol=1e-6)
     np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
+
+
+def test_oracle_search_does_not_depend_on_the_score_block_bound():
+    """bench.py times the CPU path with 8 GB score blocks, the tests with 1 GB: the chunking of
+    the queries must not change a neighbour; the scores may move in the last bit (ATen picks different GEMM kernels
+    and summation orders for different batch heights -- the reference's own `q @ emb.T` does the same)."""
+    rng = np.random.default_rng(3)
+    emb = torch.from_numpy(rng.standard_normal((3000, 48)).astype(np.float32))
+    q = torch.from_numpy(rng.standard_normal((37, 48)).astype(np.float32))
+    for metric in ("cosine", "euclidean"):
+        built = oracle.bruteforce_build(emb, metric)
+        d0, i0 = oracle.bruteforce_search(built, q, 7, metric)
+        for cb in (4 * 3000 * 1, 4 * 3000 * 5, 1 << 34):  # one query per block, five, everything at once
+            d, i = oracle.bruteforce_search(built, q, 7, metric, chunk_bytes=cb)
+            np.testing.assert_array_equal(i, i0)
+            np.testing.assert_allclose(d, d0, rtol=0, atol=2e-6 if metric == "euclidean" else 3e-7)
