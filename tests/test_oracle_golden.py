@@ -206,4 +206,4 @@ def test_oracle_search_does_not_depend_on_the_score_block_bound():
         for cb in (4 * 3000 * 1, 4 * 3000 * 5, 1 << 34):  # one query per block, five, everything at once
             d, i = oracle.bruteforce_search(built, q, 7, metric, chunk_bytes=cb)
             np.testing.assert_array_equal(i, i0)
-            np.testing.assert_allclose(d, d0, rtol=0, atol=2e-6 if metric == "euclidean" else 3e-7)
+            np.testing.assert_allclose(d, d0, rtol=2e-6, atol=3e-7)  # a few ulp
