@@ -392,6 +392,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     // (KSEL 1 is the same selector with plain stores: no policy operand in the append blocks; the
     // compactions, which are rare, keep hinted stores with the normal policy)
     const uint64_t keep_policy = KSEL == 0 ? ptx::policy_evict_last() : ptx::policy_evict_normal();
+#ifdef LK_EPI_PROF
+    long long prof_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // tfull wait, tmem ld, fast math, select, unit total, hit turns, turns, units
+    const long long prof_begin = clock64();
+#endif
     float thr = INFINITY;
     float q_sd = 0.f;
     int* cnt_out = nullptr;
@@ -442,11 +446,18 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 #pragma unroll
         for (int j = 0; j < kColsPerWarp / 32; ++j) ns[j] = sp[lane + 32 * j];
       }
+#ifdef LK_EPI_PROF
+      const long long tp0 = clock64();
+#endif
       if (!__all_sync(0xffffffffu, ptx::mbar_wait(tfull_bar(acc.idx), acc.phase))) {
         fail(kErrEpiTmemFull);
         break;
       }
       ptx::tc_fence_after();
+#ifdef LK_EPI_PROF
+      const long long tp1 = clock64();
+      prof_t[0] += tp1 - tp0;
+#endif
       const float* sd = my_side + slot * kColsPerWarp;
       const int32_t row0 = cb * kUnitCols + ch * kColsPerWarp;
       // Fast path (branch-free, a few hundred instructions in total so it stays in the
@@ -546,9 +557,16 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         uint32_t r0[32], r1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                (uint32_t)(acc.idx * kUnitCols + ch * kColsPerWarp + chunk * 32);
+#ifdef LK_EPI_PROF
+        const long long tq0 = clock64();
+#endif
         ptx::tmem_ld32(taddr, r0);
         ptx::tmem_ld32(taddr + 32u, r1);
         ptx::tmem_wait_ld();
+#ifdef LK_EPI_PROF
+        const long long tq1 = clock64();
+        prof_t[1] += tq1 - tq0;
+#endif
         if (p.debug_tile != nullptr && u == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -561,9 +579,24 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         float mg0[4], mg1[4];
         group_max(r0, sdc, mg0);
         group_max(r1, sdc + 32, mg1);
+#ifdef LK_EPI_PROF
+        const bool any_hit = __any_sync(0xffffffffu, fmaxf(fmaxf(mg0[0], mg0[1]), fmaxf(mg0[2], mg0[3])) > thr ||
+                                                         fmaxf(fmaxf(mg1[0], mg1[1]), fmaxf(mg1[2], mg1[3])) > thr);
+        const long long tq2 = clock64();
+        prof_t[2] += tq2 - tq1;
+#endif
         select(chunk, taddr, r0, sdc, mg0);
         select(chunk + 1, taddr + 32u, r1, sdc + 32, mg1);
+#ifdef LK_EPI_PROF
+        prof_t[3] += clock64() - tq2;
+        prof_t[5] += any_hit ? 1 : 0;
+        prof_t[6] += 1;
+#endif
       }
+#ifdef LK_EPI_PROF
+      prof_t[4] += clock64() - tp1;
+      prof_t[7] += 1;
+#endif
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // the accumulator stage goes back to the (leader's) MMA warp
@@ -611,6 +644,13 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       qt = nqt;
       cb = ncb;
     }
+#ifdef LK_EPI_PROF
+    if (p.debug_tile != nullptr && ew == 0 && lane == 0) {
+      long long* o = reinterpret_cast<long long*>(p.debug_tile) + (int64_t)blockIdx.x * 10;
+      for (int i = 0; i < 8; ++i) o[i] = prof_t[i];
+      o[8] = clock64() - prof_begin;
+    }
+#endif
   }
 
   // ===================== teardown =====================
