@@ -50,7 +50,10 @@ constexpr int kPFirstEpi = 4, kPEpiWarps = 8;
 constexpr int kPFirstCvt = 12, kPCvtWarps = 8;
 constexpr int kPMaxStages = 8, kPMaxKb0 = 6;
 constexpr int kHalfSlab = kSlabBytes / 2;  // this CTA's 64 rows of a (hidden chunk, K block) slab of W0
-constexpr int kStageKb = 2;                // K blocks per W0 stage: one barrier wait and one commit per 8 MMAs (the
+#ifndef LK_AE_STAGE_KB
+#define LK_AE_STAGE_KB 2
+#endif
+constexpr int kStageKb = LK_AE_STAGE_KB;   // K blocks per W0 stage: one barrier wait and one commit per 8 MMAs (the
                                            // issuing thread, not the tensor pipe, was the bottleneck at one K block)
 constexpr int kPStageBytes = kStageKb * kHalfSlab;
 constexpr int kPHeader = 1024;

@@ -503,6 +503,21 @@ def test_faiss_index_persistence(lrb, tmp_path):
     assert r2.index.size == 50 and len(r2._texts) == 50
 
 
+def test_documented_incompatibilities_fail_loudly(lrb):
+    """top-k above LK_MAX_K names the limit (the reference takes any k), and a retriever
+    built with keep_source=False has no `.emb` to hand out (the corpus only exists as tiles in HBM)."""
+    emb = inputs.reference_test_embeddings(6000, 32)
+    r = lrb.BruteForceRetriever(emb, [""] * 6000, None, metric="cosine", keep_source=False)
+    d, i = r.search(emb[:3], 4096)  # the deepest supported search
+    assert d.shape == (3, 4096) and (np.diff(d, axis=1) <= 0).all()
+    with pytest.raises(ValueError, match="LK_MAX_K"):
+        r.search(emb[:3], 5000)
+    with pytest.raises(AttributeError, match="keep_source"):
+        r.emb
+    r2 = lrb.BruteForceRetriever(emb, [""] * 6000, None, metric="cosine")
+    assert torch.allclose(r2.emb, torch.nn.functional.normalize(emb, dim=1))  # bruteforce.py:49-50
+
+
 def test_truncated_or_corrupt_index_file_starts_clean(lrb, tmp_path):
     """a truncated image (a crash mid-save) or a header that lies about its payload must
     take the reference's 'corrupted file -> start clean' route (FAISSEmbeddingRetriever.py:70-73),
