@@ -54,6 +54,7 @@ def _worker(rank, world, port, metric, k, exchange, out_dir):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("metric,k", [("cosine", 10), ("euclidean", 32), ("mahalanobis", 10),
+                                      ("euclidean", 100),  # config 4's selector: append buffers + 100 candidates per rank
                                       ("cosine", 300)])  # above 128: slab search per shard, all-gather + sorting merge
 def test_sharded_search_two_gpus(tmp_path, metric, k, exchange):
     import oracle
