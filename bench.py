@@ -75,17 +75,19 @@ def parse_args():
 
 
 def traffic_ratios():
-    """measured DRAM bytes / algorithmic bytes of the search kernel (ncu, profiles/r01_traffic.json)"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        return float(t["batch1"]["ratio"]), float(t["batch4096"]["ratio"])
-    except Exception:
-        return None, None
+    """measured DRAM bytes / algorithmic bytes of the search kernel (ncu, profiles/r02_traffic.json)"""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            return float(t["batch1"]["ratio"]), float(t["batch4096"]["ratio"])
+        except Exception:
+            continue
+    return None, None
 
 
 TRAFFIC_SRC = ("estimated: this shape's algorithmic bytes x the DRAM/algorithmic ratio ncu measured for the same "
-               "kernel on a 10M-row (batch 1) / 4M-row (batch 4096) run, profiles/r01_traffic.json; not captured "
+               "kernel on a 10M-row (batch 1) / 4M-row (batch 4096) run, profiles/r02_traffic.json; not captured "
                "in this run")
 
 
