@@ -37,9 +37,12 @@ namespace lk {
 
 namespace {
 
-constexpr int kThreads = 384;
+#ifndef LK_EPI_WARPS
+#define LK_EPI_WARPS 8  // experiment: 16 = four epilogue warps per lane quarter, 64 columns each, one chunk per turn
+#endif
+constexpr int kThreads = 128 + 32 * LK_EPI_WARPS;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = LK_EPI_WARPS;
 constexpr int kColSplit = kEpiWarps / 4;                 // epilogue warps per lane quarter
 constexpr int kUnitBlocks = 2;                           // row blocks per unit
 constexpr int kUnitCols = kUnitBlocks * kBlockRows;      // 256 accumulator columns per unit
@@ -552,6 +555,20 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       // Two chunks per turn: both tcgen05.ld are in flight together and the two independent
       // score / max chains interleave, which hides most of the latency two warps per scheduler
       // cannot; the selection steps then run in row order.
+#if LK_EPI_WARPS > 8
+#pragma unroll 1
+      for (int chunk = 0; chunk < kColsPerWarp / 32; ++chunk) {  // one chunk per turn: 96 registers per thread
+        uint32_t r0[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                               (uint32_t)(acc.idx * kUnitCols + ch * kColsPerWarp + chunk * 32);
+        ptx::tmem_ld32(taddr, r0);
+        ptx::tmem_wait_ld();
+        const float* sdc = sd + chunk * 32;
+        float mg0[4];
+        group_max(r0, sdc, mg0);
+        select(chunk, taddr, r0, sdc, mg0);
+      }
+#else
 #pragma unroll 1
       for (int chunk = 0; chunk < kColsPerWarp / 32; chunk += 2) {
         uint32_t r0[32], r1[32];
@@ -596,6 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
 #ifdef LK_EPI_PROF
       prof_t[4] += clock64() - tp1;
       prof_t[7] += 1;
+#endif
 #endif
       ptx::tc_fence_before();
       __syncwarp();
