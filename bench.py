@@ -21,6 +21,7 @@ arithmetic timed beside it on a bounded sample:
   c3_b*      Mahalanobis top-10 over 10M x 384 anisotropic rows, batch 1 / 64 / 4096
   c4_b*      Euclidean top-100 over 10M x 768, batch 1 / 64 / 4096 -- on N > 1 GPUs row-sharded through
              ShardedRetriever (the only side config run at N > 1)
+under "batch_sweep" the points of config 5's batch sweep between its two ends (4, 16, 64, 256, 1024 queries),
 and under "checks" an ORACLE comparison of the sharded data path run by this very process group:
 a 1M-row side index sharded over the N ranks against oracle.bruteforce_search on rank 0.
 """
@@ -756,6 +757,20 @@ def main():
     _, ms1_e2e, _ = ctx.timed(lambda q: case.step_e2e(q, k), q1_pin, args.batch1_steps, 1)
     kms1, kms1_ranks = ctx.kernel_ms(index, q1_dev, k, lo, args.batch1_steps)
 
+    # the batch sweep of config 5 between its two end points (powers of 4): device-timed step + search kernel
+    sweep = {}
+    rows_per_gpu_s = -(-args.rows // world)
+    for bs in (4, 16, 64, 256, 1024):
+        if bs >= args.batch:
+            continue
+        qs = q_dev[:bs].contiguous()
+        ms_s, _, _ = ctx.timed(lambda q: case.step_device(q, k), qs, 5, 3)
+        kms_s, _ = ctx.kernel_ms(index, qs, k, lo, 3)
+        tf_s = 2.0 * bs * rows_per_gpu_s * args.dim / (kms_s * 1e-3) / 1e12
+        gb_s = (rows_per_gpu_s * args.dim * 2 + rows_per_gpu_s * 4) / (kms_s * 1e-3) / 1e9
+        sweep[f"b{bs}"] = {"qps": bs / (ms_s * 1e-3), "ms_per_step": ms_s, "kernel_ms": kms_s,
+                           "hbm_frac_one_pass": gb_s / pk["hbm_gbs"], "tensor_frac_sustained": tf_s / pk["bf16_tflops_sustained"]}
+
     # ---- full-size correctness properties (outside the timed regions) -----------------
     case.check()  # no search kernel hit a pipeline timeout, no rank timed out waiting for a peer's candidates
     d_fin, i_fin = out[0].cpu().numpy(), out[1].cpu().numpy()
@@ -824,6 +839,7 @@ def main():
                                     "traffic": None if r1 is None else r1 * bytes_per_launch, "traffic_src": TRAFFIC_SRC,
                                     "kernel_ms": kms1, "kernel_ms_per_rank": kms1_ranks,
                                     "bytes_per_launch": bytes_per_launch, "peak_src": pk["src"]}},
+            "batch_sweep": sweep,
             "clocks": clocks,
             "checks": checks,
             "build_s": build_s,
