@@ -373,7 +373,10 @@ int lk_index_check(lk_index* ix) {
   if (!ix) return LK_ERR_INVALID;
   DeviceGuard guard(ix->device);
   int flag = 0;
-  LK_CUDA(cudaMemcpy(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));  // synchronises
+  // every stream of the device: a plain cudaMemcpy only orders behind blocking streams, and torch's side streams are
+  // cudaStreamNonBlocking (a search still running on one would be read as "no timeout")
+  LK_CUDA(cudaDeviceSynchronize());
+  LK_CUDA(cudaMemcpy(&flag, ix->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag != 0) {
     cudaMemset(ix->err_flag, 0, sizeof(int));
     set_error("search kernel pipeline timed out (barrier code %d); results are invalid", flag);

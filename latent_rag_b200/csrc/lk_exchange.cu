@@ -384,6 +384,7 @@ int lk_comm_check(lk_comm* c) {
   if (!c) return LK_ERR_INVALID;
   DevGuard guard(c->device);
   int flag = 0;
+  LK_CUDA(cudaDeviceSynchronize());  // non-blocking streams too (a plain cudaMemcpy would not wait for them)
   LK_CUDA(cudaMemcpy(&flag, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag != 0) {
     cudaMemset(c->err_flag, 0, sizeof(int));

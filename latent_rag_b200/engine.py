@@ -46,7 +46,8 @@ class ExactIndex:
 
     metric   "cosine" | "euclidean" | "mahalanobis"
     storage  "bf16" (tcgen05 path; scores are those of the reference fed bf16-rounded
-             inputs) | "fp32" (exact fp32 FMA path)
+             inputs) | "fp32" (fp32-level scores: split-bf16 planes on the tensor cores for
+             b * rows >= 2^20, the fp32 FMA kernel below that)
     whiten   for mahalanobis: [dim, dim] fp64 L with precision = L @ L.T
     """
 
