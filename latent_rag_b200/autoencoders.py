@@ -136,7 +136,10 @@ class _FusedEncoder:
         x2 = x.reshape(-1, self.input_dim)
         if x2.is_cuda and x2.device.index != self.device:
             x2 = x2.to(f"cuda:{self.device}")
-        z = torch.empty((x2.size(0), self.latent_dim), dtype=torch.float32, device=x2.device)
+        # host rows -> host latents (retrieval/embedder.py:24-48 returns CPU fp32): page-locked, so that the
+        # device -> host copies of the chunks run at link speed under the kernels of the next ones
+        z = torch.empty((x2.size(0), self.latent_dim), dtype=torch.float32, device=x2.device,
+                        pin_memory=not x2.is_cuda)
         mem = nat.LK_DEVICE if x2.is_cuda else nat.LK_HOST
         stream = int(torch.cuda.current_stream(self.device).cuda_stream)
         nat.check(self._lib.lk_ae_encode(h, c_void_p(x2.data_ptr()), mem, x2.size(0), c_void_p(z.data_ptr()), mem,

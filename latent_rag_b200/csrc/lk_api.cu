@@ -95,7 +95,12 @@ struct lk_ae {
   float *w0t = nullptr, *b0 = nullptr, *w1t = nullptr, *b1 = nullptr;
   unsigned char *w0_slabs = nullptr, *w1_slabs = nullptr;
   int* err_flag = nullptr;
-  Buf xin, zout, xslabs;
+  Buf xslabs;
+  // host inputs / outputs: two staging buffers each way, copies on their own streams so that the upload of chunk
+  // i + 1 and the download of chunk i - 1 run under the kernel of chunk i
+  Buf xin[2], zout[2];
+  cudaStream_t cs_in = nullptr, cs_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 extern "C" {
@@ -922,8 +927,14 @@ int lk_ae_destroy(lk_ae* ae) {
   if (ae->w0_slabs) cudaFree(ae->w0_slabs);
   if (ae->w1_slabs) cudaFree(ae->w1_slabs);
   if (ae->err_flag) cudaFree(ae->err_flag);
-  ae->xin.release();
-  ae->zout.release();
+  for (int i = 0; i < 2; ++i) {
+    ae->xin[i].release();
+    ae->zout[i].release();
+    for (cudaEvent_t e : {ae->ev_in[i], ae->ev_comp[i], ae->ev_out[i]})
+      if (e) cudaEventDestroy(e);
+  }
+  if (ae->cs_in) cudaStreamDestroy(ae->cs_in);
+  if (ae->cs_out) cudaStreamDestroy(ae->cs_out);
   ae->xslabs.release();
   delete ae;
   return LK_OK;
@@ -1010,6 +1021,39 @@ int lk_ae_set_precision(lk_ae* ae, int precision) {
   return LK_OK;
 }
 
+// one chunk of rows, device to device, on `st`
+static int ae_encode_rows(lk_ae* ae, const float* xin, int64_t cnt, float* zdev, bool use_umma, cudaStream_t st) {
+  const int l2 = ae->kind == LK_AE_CAE ? 1 : 0;
+  const char* pe = getenv("LK_AE_PAIR");  // bring-up override: 0 = the single-CTA kernel for bf16 operands too
+  const bool use_pair = use_umma && ae->precision == LK_BF16 && !(pe && !atoi(pe)) &&
+                        ae_pair_supported(ae->d_in, ae->d_hidden, ae->d_latent, ae->sm_count) &&
+                        (reinterpret_cast<uintptr_t>(xin) & 31u) == 0;
+  if (use_pair)  // bf16 operands: CTA pairs, the fp32 rows are rounded inside the kernel (no split pass)
+    return launch_ae_pair(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs, ae->w1_slabs, ae->b0, ae->b1, l2,
+                          zdev, ae->err_flag, ae->sm_count, st);
+  if (use_umma) {
+    int rc = ae->xslabs.ensure(ae_umma_x_slab_bytes(cnt, ae->d_in));
+    if (rc != LK_OK) return rc;
+    const int planes = ae->precision == LK_BF16 ? 1 : 2;
+    if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, planes, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;
+    return launch_ae_umma(ae->xslabs.as<unsigned char>(), cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs,
+                          ae->w1_slabs, ae->b0, ae->b1, l2, planes, zdev, ae->err_flag, ae->sm_count, st);
+  }
+  return launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1, l2, zdev, st);
+}
+
+static int ae_check_flag(lk_ae* ae) {
+  if (!ae->err_flag) return LK_OK;
+  int flag = 0;
+  LK_CUDA(cudaMemcpy(&flag, ae->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag != 0) {
+    cudaMemset(ae->err_flag, 0, sizeof(int));
+    set_error("autoencoder kernel pipeline timed out (barrier code %d); results are invalid", flag);
+    return LK_ERR_CUDA;
+  }
+  return LK_OK;
+}
+
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream) {
   if (!ae || m < 0 || (m > 0 && (!x || !z)) || (x_mem != LK_HOST && x_mem != LK_DEVICE) ||
       (z_mem != LK_HOST && z_mem != LK_DEVICE)) {
@@ -1019,8 +1063,6 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
   if (m == 0) return LK_OK;
   DeviceGuard guard(ae->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int l2 = ae->kind == LK_AE_CAE ? 1 : 0;
-  const int64_t step = 1 << 18;
   int rc;
   // AUTO: tensor cores once there are two full row tiles of work, fp32 FMA for small batches
   const char* env = getenv("LK_AE_KERNEL");
@@ -1029,55 +1071,70 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
   if (env && !strcmp(env, "umma")) which = LK_KERNEL_UMMA;
   const bool use_umma = ae->w0_slabs && (which == LK_KERNEL_UMMA || ae->precision == LK_BF16 ||
                                          (which == LK_KERNEL_AUTO && m >= 2 * kBlockRows));
-  for (int64_t done = 0; done < m; done += step) {
-    const int64_t cnt = m - done < step ? m - done : step;
-    const float* xin = x + (size_t)done * ae->d_in;
-    float* zo = z + (size_t)done * ae->d_latent;
-    if (x_mem == LK_HOST) {
-      if ((rc = ae->xin.ensure((size_t)step * ae->d_in * 4)) != LK_OK) return rc;
-      LK_CUDA(cudaMemcpyAsync(ae->xin.p, xin, (size_t)cnt * ae->d_in * 4, cudaMemcpyHostToDevice, st));
-      xin = ae->xin.as<float>();
+  const bool host_in = x_mem == LK_HOST, host_out = z_mem == LK_HOST;
+  if (!host_in && !host_out) {  // device to device: chunks only bound the split-plane scratch
+    const int64_t step = 1 << 18;
+    for (int64_t done = 0; done < m; done += step) {
+      const int64_t cnt = m - done < step ? m - done : step;
+      if ((rc = ae_encode_rows(ae, x + (size_t)done * ae->d_in, cnt, z + (size_t)done * ae->d_latent, use_umma, st)) != LK_OK)
+        return rc;
     }
-    float* zdev = zo;
-    if (z_mem == LK_HOST) {
-      if ((rc = ae->zout.ensure((size_t)step * ae->d_latent * 4)) != LK_OK) return rc;
-      zdev = ae->zout.as<float>();
-    }
-    const char* pe = getenv("LK_AE_PAIR");  // bring-up override: 0 = the single-CTA kernel for bf16 operands too
-    const bool use_pair = use_umma && ae->precision == LK_BF16 && !(pe && !atoi(pe)) &&
-                          ae_pair_supported(ae->d_in, ae->d_hidden, ae->d_latent, ae->sm_count) &&
-                          (reinterpret_cast<uintptr_t>(xin) & 31u) == 0;
-    if (use_pair) {
-      // bf16 operands: CTA pairs, the fp32 rows are rounded inside the kernel (no split pass)
-      rc = launch_ae_pair(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs, ae->w1_slabs, ae->b0, ae->b1, l2,
-                          zdev, ae->err_flag, ae->sm_count, st);
-    } else if (use_umma) {
-      if ((rc = ae->xslabs.ensure(ae_umma_x_slab_bytes(step, ae->d_in))) != LK_OK) return rc;
-      const int planes = ae->precision == LK_BF16 ? 1 : 2;
-      if ((rc = launch_ae_split_rows(xin, cnt, ae->d_in, planes, ae->xslabs.as<unsigned char>(), st)) != LK_OK) return rc;
-      rc = launch_ae_umma(ae->xslabs.as<unsigned char>(), cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0_slabs,
-                          ae->w1_slabs, ae->b0, ae->b1, l2, planes, zdev, ae->err_flag, ae->sm_count, st);
-    } else {
-      rc = launch_ae_encode(xin, cnt, ae->d_in, ae->d_hidden, ae->d_latent, ae->w0t, ae->b0, ae->w1t, ae->b1,
-                            l2, zdev, st);
-    }
-    if (rc != LK_OK) return rc;
-    if (z_mem == LK_HOST)
-      LK_CUDA(cudaMemcpyAsync(zo, zdev, (size_t)cnt * ae->d_latent * 4, cudaMemcpyDeviceToHost, st));
-    if (x_mem == LK_HOST || z_mem == LK_HOST) {
-      LK_CUDA(cudaStreamSynchronize(st));
-      if (ae->err_flag) {
-        int flag = 0;
-        LK_CUDA(cudaMemcpy(&flag, ae->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag != 0) {
-          cudaMemset(ae->err_flag, 0, sizeof(int));
-          set_error("autoencoder kernel pipeline timed out (barrier code %d); results are invalid", flag);
-          return LK_ERR_CUDA;
-        }
-      }
+    return LK_OK;
+  }
+
+  // Host rows and / or host latents: chunks of 32 Ki rows (48 MiB of fp32 input at 384 dims) through two staging
+  // buffers each way.  H2D of chunk i + 1 (cs_in) and D2H of chunk i - 1 (cs_out) run under the kernel of chunk i
+  // (the caller's stream); a buffer is reused two chunks later, behind the event of its previous consumer.
+  const int64_t step = 1 << 15;
+  if (!ae->cs_in) {
+    LK_CUDA(cudaStreamCreateWithFlags(&ae->cs_in, cudaStreamNonBlocking));
+    LK_CUDA(cudaStreamCreateWithFlags(&ae->cs_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      LK_CUDA(cudaEventCreateWithFlags(&ae->ev_in[i], cudaEventDisableTiming));
+      LK_CUDA(cudaEventCreateWithFlags(&ae->ev_comp[i], cudaEventDisableTiming));
+      LK_CUDA(cudaEventCreateWithFlags(&ae->ev_out[i], cudaEventDisableTiming));
     }
   }
-  return LK_OK;
+  const int64_t n_chunks = (m + step - 1) / step;
+  const int64_t rows_buf = m < step ? m : step;
+  for (int i = 0; i < (n_chunks > 1 ? 2 : 1); ++i) {
+    if (host_in && (rc = ae->xin[i].ensure((size_t)rows_buf * ae->d_in * 4)) != LK_OK) return rc;
+    if (host_out && (rc = ae->zout[i].ensure((size_t)rows_buf * ae->d_latent * 4)) != LK_OK) return rc;
+  }
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int buf = (int)(c & 1);
+    const int64_t done = c * step, cnt = m - done < step ? m - done : step;
+    const float* xin = x + (size_t)done * ae->d_in;
+    float* zo = z + (size_t)done * ae->d_latent;
+    if (host_in) {
+      if (c >= 2) LK_CUDA(cudaStreamWaitEvent(ae->cs_in, ae->ev_comp[buf], 0));  // the kernel of chunk c - 2 read xin[buf]
+      LK_CUDA(cudaMemcpyAsync(ae->xin[buf].p, xin, (size_t)cnt * ae->d_in * 4, cudaMemcpyHostToDevice, ae->cs_in));
+      LK_CUDA(cudaEventRecord(ae->ev_in[buf], ae->cs_in));
+      LK_CUDA(cudaStreamWaitEvent(st, ae->ev_in[buf], 0));
+      xin = ae->xin[buf].as<float>();
+    }
+    float* zdev = zo;
+    if (host_out) {
+      if (c >= 2) LK_CUDA(cudaStreamWaitEvent(st, ae->ev_out[buf], 0));  // zout[buf] of chunk c - 2 is on the host
+      zdev = ae->zout[buf].as<float>();
+    }
+    if ((rc = ae_encode_rows(ae, xin, cnt, zdev, use_umma, st)) != LK_OK) {
+      cudaStreamSynchronize(ae->cs_in);
+      cudaStreamSynchronize(ae->cs_out);
+      cudaStreamSynchronize(st);
+      return rc;
+    }
+    LK_CUDA(cudaEventRecord(ae->ev_comp[buf], st));
+    if (host_out) {
+      LK_CUDA(cudaStreamWaitEvent(ae->cs_out, ae->ev_comp[buf], 0));
+      LK_CUDA(cudaMemcpyAsync(zo, zdev, (size_t)cnt * ae->d_latent * 4, cudaMemcpyDeviceToHost, ae->cs_out));
+      LK_CUDA(cudaEventRecord(ae->ev_out[buf], ae->cs_out));
+    }
+  }
+  // the caller may free x and read z on return
+  LK_CUDA(cudaStreamSynchronize(st));
+  if (host_out) LK_CUDA(cudaStreamSynchronize(ae->cs_out));
+  return ae_check_flag(ae);
 }
 
 }  // extern "C"

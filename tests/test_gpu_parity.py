@@ -746,6 +746,25 @@ def test_ae_pair_kernel_ragged_sizes(lrb, m, monkeypatch):
         assert e1.max().item() < 2e-3 and (e1 > 2e-5).float().mean().item() < 0.02
 
 
+@pytest.mark.parametrize("precision,kernel", [("bf16", "auto"), ("fp32", "auto"), ("fp32", "simt")])
+def test_ae_host_rows_go_through_the_chunk_pipeline(lrb, precision, kernel):
+    """Host rows in / host latents out (retrieval/embedder.py:24-48 returns CPU fp32) are cut into 32 Ki-row chunks whose
+    uploads, kernels and downloads overlap on three streams through two staging buffers each way: four chunks with a
+    ragged last one (every buffer reused), pageable and page-locked inputs -- bit-equal to the device-to-device call."""
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    rng = np.random.default_rng(17)
+    m = 3 * 32768 + 1699
+    x = torch.from_numpy(rng.standard_normal((m, 384)).astype(np.float32))
+    ae = lrb.load_autoencoder("cae", os.path.join(gold, "ae_weights_cae.npz")).set_precision(precision).set_kernel(kernel)
+    z_dev = ae.encode(x.cuda()).cpu()
+    z_pageable = ae.encode(x)
+    z_pinned = ae.encode(x.pin_memory())
+    assert not z_pageable.is_cuda and z_pageable.is_pinned()
+    np.testing.assert_array_equal(z_pageable.numpy(), z_dev.numpy())
+    np.testing.assert_array_equal(z_pinned.numpy(), z_dev.numpy())
+    np.testing.assert_array_equal(ae.encode(x[:40_000]).numpy(), z_dev[:40_000].numpy())  # two chunks, a second call
+
+
 @pytest.mark.parametrize("d_in,d_hidden,d_latent", [(64, 128, 16), (128, 256, 48), (384, 512, 64), (256, 1024, 33)])
 def test_ae_pair_kernel_other_dims(lrb, d_in, d_hidden, d_latent):
     rng = np.random.default_rng(d_in + d_latent)
