@@ -577,11 +577,11 @@ def cfg_c2(ctx: Ctx, sample, scale):
     m_e = min(m, 262_144)
     xh = x[:m_e].cpu().pin_memory()
     ae.set_precision("fp32")
-    ae.encode(xh[:1024])
+    ae.encode(xh)  # (the first call of a size allocates the staging buffers and the page-locked result block)
     t0 = time.perf_counter()
-    for _ in range(3):
+    for _ in range(5):
         ae.encode(xh)
-    e2e_s = (time.perf_counter() - t0) / 3
+    e2e_s = (time.perf_counter() - t0) / 5
     enc["e2e"] = {"value": m_e / e2e_s, "unit": "vectors/s", "vectors": m_e, "h2d_bytes_per_step": m_e * 384 * 4,
                   "d2h_bytes_per_step": m_e * 64 * 4}
     if sample is not None:
