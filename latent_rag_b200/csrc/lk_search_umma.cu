@@ -78,6 +78,8 @@ struct UmmaParams {
   int nblk;              // row-block PAIRS in the corpus (units per query tile)
   int nkb;               // K blocks of 64 the MMA loop runs over per unit (split mode: 3 * split_n)
   int nkb_q;             // K-block slabs of a query tile in memory (= nkb; split mode: 2 * split_n)
+  int nkb_res;           // the first nkb_res of them stay in shared memory for a whole segment (QRES: all of them);
+                         // the others travel through the pipeline stages next to the corpus slabs of their K step
   int split_n;           // 0, or the K blocks per PLANE of split-bf16 operands (fp32 storage): rows and queries
                          // are stored as [hi plane | lo plane] and step kb multiplies q(hi,hi,lo) by e(hi,lo,hi)
   int n_stages;
@@ -161,7 +163,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
   float* side_ring = reinterpret_cast<float*>(smem + kBarBytes);
   unsigned char* q_sm = smem + kHeaderBytes;
   q_sm += (1024u - (ptx::smem_u32(q_sm) & 1023u)) & 1023u;  // swizzle atoms are 1024-byte aligned
-  unsigned char* stage_sm = q_sm + (QRES ? p.nkb_q * kKBlockBytes : 0);
+  const int n_res = QRES ? p.nkb_q : p.nkb_res;  // query K blocks resident for a segment
+  const bool res = QRES || n_res > 0;
+  unsigned char* stage_sm = q_sm + n_res * kKBlockBytes;
   constexpr int kSlabsPerStage = kUnitBlocks / CG;  // corpus row blocks this CTA loads per K block
   constexpr int kStageBytes = (QRES ? kSlabsPerStage : kSlabsPerStage + 1) * kKBlockBytes;
 
@@ -227,14 +231,14 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     const uint64_t stream_policy = ptx::policy_evict_first();
     for (int64_t u = u0; u < u1 && ok; ++u) {
       const unsigned char* q_src = p.q_tiles + (int64_t)qt * p.block_bytes;
-      if (QRES && (u == u0 || b == 0)) {
+      if (res && (u == u0 || b == 0)) {
         if (seg > 0 && !__all_sync(0xffffffffu, ptx::mbar_wait(qempty_bar, (uint32_t)((seg - 1) & 1)))) {
           fail(kErrProdQEmpty);
           break;
         }
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(p.nkb_q * kKBlockBytes));
-          for (int kb = 0; kb < p.nkb_q; ++kb)
+          ptx::mbar_arrive_expect_tx(qfull_bar, (uint32_t)(n_res * kKBlockBytes));
+          for (int kb = 0; kb < n_res; ++kb)
             ptx::bulk_g2s(ptx::smem_u32(q_sm + kb * kKBlockBytes), q_src + (int64_t)kb * kKBlockBytes,
                           kKBlockBytes, qfull_bar);
         }
@@ -248,16 +252,17 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
           ok = false;
           break;
         }
+        const bool q_streamed = !QRES && q_kb(kb) >= n_res;  // this K step's query slab rides in the stage
         if (ptx::elect_one()) {
           const uint32_t dst = ptx::smem_u32(stage_sm + st.idx * kStageBytes);
-          ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)kStageBytes);
+          ptx::mbar_arrive_expect_tx(full_bar(st.idx), (uint32_t)((kSlabsPerStage + (q_streamed ? 1 : 0)) * kKBlockBytes));
 #pragma unroll
           for (int h = 0; h < kSlabsPerStage; ++h) {  // rows 0-127 and 128-255 of the N=256 operand (CG=2: this CTA's half)
             const unsigned char* src = e_src + (h + rank * kSlabsPerStage) * p.block_bytes + (int64_t)e_kb(kb) * kKBlockBytes;
             if (stream_once) ptx::bulk_g2s_hint(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx), stream_policy);
             else ptx::bulk_g2s(dst + h * kKBlockBytes, src, kKBlockBytes, full_bar(st.idx));
           }
-          if (!QRES)
+          if (q_streamed)
             ptx::bulk_g2s(dst + kSlabsPerStage * kKBlockBytes, q_src + (int64_t)q_kb(kb) * kKBlockBytes, kKBlockBytes,
                           full_bar(st.idx));
         }
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
     int b = (int)(u0 % p.nblk);
     bool ok = true;
     for (int64_t u = u0; u < u1 && ok; ++u) {
-      if (QRES && (u == u0 || b == 0)) {
+      if (res && (u == u0 || b == 0)) {
         if (!__all_sync(0xffffffffu, ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1)))) {
           fail(kErrRelayQFull);
           break;
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         fail(kErrMmaTmemEmpty);
         break;
       }
-      if (QRES && (u == u0 || b == 0)) {
+      if (res && (u == u0 || b == 0)) {
         if (!__all_sync(0xffffffffu, ptx::mbar_wait(qfull_bar, (uint32_t)(seg & 1)))) {
           fail(kErrMmaQFull);
           break;
@@ -343,8 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
         }
         ptx::tc_fence_after();
         const uint32_t e_lo = st_base + (uint32_t)(st.idx * (kStageBytes >> 4));
-        const uint32_t q_lo = QRES ? q_base + (uint32_t)(q_kb(kb) * (kKBlockBytes >> 4))
-                                   : e_lo + (uint32_t)(kSlabsPerStage * (kKBlockBytes >> 4));
+        const uint32_t q_lo = (QRES || q_kb(kb) < n_res) ? q_base + (uint32_t)(q_kb(kb) * (kKBlockBytes >> 4))
+                                                         : e_lo + (uint32_t)(kSlabsPerStage * (kKBlockBytes >> 4));
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kKBlockElems / 16; ++k) {  // +32 bytes per K step inside the swizzled row
@@ -365,10 +370,10 @@ __global__ void __launch_bounds__(kThreads, 1) umma_search_kernel(const UmmaPara
       if (ptx::elect_one()) {
         if (CG == 2) {
           ptx::umma_commit_2cta(tfull_bar(acc.idx), 3);              // accumulators complete -> both epilogues
-          if (QRES && seg_end) ptx::umma_commit_2cta(qempty_bar, 3);  // query tiles no longer read
+          if (res && seg_end) ptx::umma_commit_2cta(qempty_bar, 3);  // query tiles no longer read
         } else {
           ptx::umma_commit(tfull_bar(acc.idx));
-          if (QRES && seg_end) ptx::umma_commit(qempty_bar);
+          if (res && seg_end) ptx::umma_commit(qempty_bar);
         }
       }
       __syncwarp();
@@ -687,8 +692,25 @@ inline bool q_resident(const TileGeom& g) { return n_kblocks(g) <= 8; }
 inline int stage_bytes_for(const TileGeom& g, int cg) {
   return (kUnitBlocks / cg + (q_resident(g) ? 0 : 1)) * kKBlockBytes;
 }
+// Query K blocks kept in shared memory for a whole segment.  All of them when the tile fits beside the pipeline
+// (<= 8 K blocks: 512 bf16 dimensions).  Otherwise the tile is streamed with the corpus, which doubles the L2 -> SM
+// traffic of a CTA pair's unit; at thousands of queries that traffic (9.8 TB/s over the 148 SMs, ncu, 768-d) and not
+// the tensor pipe bounds the kernel, so CTA pairs keep the first 4 K blocks (64 KB) resident and run 4 stages of
+// 32 KB instead of 6: 2M x 768 top-100 at 4096 queries 9.70 -> 9.27 ms, fp32 planes 2M x 384 11.29 -> 10.74 ms
+// (6 resident blocks leave 3 stages: 9.9 ms).  Single CTAs (<= 128 queries, HBM-bound) keep the deeper pipeline:
+// 10M x 768 at 64 queries 2.17 -> 2.21 ms with 4 resident blocks.
+constexpr int kPartialResidentKb = 4;
+inline int n_res_for(const TileGeom& g, int cg) {
+  if (q_resident(g)) return n_kblocks(g);
+  int v = cg == 2 ? kPartialResidentKb : 0;
+  if (const char* e = getenv("LK_QRES_KB")) v = atoi(e);  // bring-up override
+  if (v < 0) v = 0;
+  const int stage = (kUnitBlocks / cg + 1) * kKBlockBytes;
+  while (v > 0 && (kSmemBudget - kHeaderBytes - kAlignSlack - v * kKBlockBytes) / stage < 3) --v;  // >= 3 stages
+  return v < n_kblocks(g) ? v : n_kblocks(g) - 1;
+}
 inline int n_stages_for(const TileGeom& g, int cg) {
-  const int q_bytes = q_resident(g) ? n_kblocks(g) * kKBlockBytes : 0;
+  const int q_bytes = n_res_for(g, cg) * kKBlockBytes;
   int s = (kSmemBudget - kHeaderBytes - kAlignSlack - q_bytes) / stage_bytes_for(g, cg);
   return s > kMaxStages ? kMaxStages : s;
 }
@@ -786,6 +808,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     set_error("tcgen05 search: split operands need 2 planes of %d K blocks, the geometry has %d", a.split_n, p.nkb_q);
     return LK_ERR_INVALID;
   }
+  p.nkb_res = n_res_for(a.g, sc.cg);
   p.n_stages = n_stages_for(a.g, sc.cg);
   p.n_lists = a.n_lists;
   p.ksel = a.ksel;
@@ -809,7 +832,7 @@ int launch_search_umma(const SearchArgs& a, int sm_count, cudaStream_t st) {
     if (v >= 2 && v <= p.n_stages) p.n_stages = v;
   }
   const bool qres = q_resident(a.g);
-  const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (qres ? (size_t)p.nkb_q * kKBlockBytes : 0) +
+  const size_t smem = (size_t)kHeaderBytes + kAlignSlack + (size_t)p.nkb_res * kKBlockBytes +
                       (size_t)p.n_stages * stage_bytes_for(a.g, sc.cg);
   const int ksel = ksel_for(a.k);
   if (ksel != a.ksel) {

@@ -17,14 +17,16 @@ ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--metric", default="cosine")
 ap.add_argument("--kernel", default="auto")
+ap.add_argument("--storage", default="bf16")
 a = ap.parse_args()
 
-ix = lrb.ExactIndex(a.dim, a.rows, metric=a.metric)
+ix = lrb.ExactIndex(a.dim, a.rows, metric=a.metric, storage=a.storage)
+dt = torch.bfloat16 if a.storage == "bf16" else torch.float32
 g = torch.Generator(device="cuda").manual_seed(1)
 for lo in range(0, a.rows, 1_000_000):
     n = min(1_000_000, a.rows - lo)
-    ix.add(torch.randn((n, a.dim), generator=g, device="cuda").to(torch.bfloat16))
-q = torch.randn((a.batch, a.dim), generator=g, device="cuda").to(torch.bfloat16)
+    ix.add(torch.randn((n, a.dim), generator=g, device="cuda").to(dt))
+q = torch.randn((a.batch, a.dim), generator=g, device="cuda").to(dt)
 ix.set_timing(True)
 for it in range(a.iters):
     ix.search(q, a.k, device_out=True, kernel=a.kernel)
