@@ -695,11 +695,12 @@ inline int stage_bytes_for(const TileGeom& g, int cg) {
 // Query K blocks kept in shared memory for a whole segment.  All of them when the tile fits beside the pipeline
 // (<= 8 K blocks: 512 bf16 dimensions).  Otherwise the tile is streamed with the corpus, which doubles the L2 -> SM
 // traffic of a CTA pair's unit; at thousands of queries that traffic (9.8 TB/s over the 148 SMs, ncu, 768-d) and not
-// the tensor pipe bounds the kernel, so CTA pairs keep the first 4 K blocks (64 KB) resident and run 4 stages of
-// 32 KB instead of 6: 2M x 768 top-100 at 4096 queries 9.70 -> 9.27 ms, fp32 planes 2M x 384 11.29 -> 10.74 ms
-// (6 resident blocks leave 3 stages: 9.9 ms).  Single CTAs (<= 128 queries, HBM-bound) keep the deeper pipeline:
-// 10M x 768 at 64 queries 2.17 -> 2.21 ms with 4 resident blocks.
-constexpr int kPartialResidentKb = 4;
+// the tensor pipe bounds the kernel, so CTA pairs keep the first 5 K blocks (80 KB) resident and run 4 stages of
+// 32 KB instead of 6 (measured back to back on one box, tools/gpu_r2_qres.sh): 2M x 768 top-100 at 4096 queries
+// 10.0 -> 9.36 ms (4 blocks: 9.5, 6 blocks = 3 stages: 9.9), fp32 planes 2M x 384 11.1 -> 10.75 ms; 512 queries lose
+// 1.5 % (1.38 -> 1.40 ms).  Single CTAs (<= 128 queries, HBM-bound) keep the deeper pipeline: 10M x 768 at 64 queries
+// 2.17 -> 2.21 ms with 4 resident blocks.
+constexpr int kPartialResidentKb = 5;
 inline int n_res_for(const TileGeom& g, int cg) {
   if (q_resident(g)) return n_kblocks(g);
   int v = cg == 2 ? kPartialResidentKb : 0;
