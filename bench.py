@@ -505,7 +505,7 @@ def cfg_c1(ctx: Ctx, sample):
         case = SearchCase(ctx, index, 0, "cosine", b)
         # (30 warm-up calls: the GPU sat idle during the CPU baseline of the headline and a 0.4 ms step does not ramp
         #  the clocks by itself)
-        rec, res, _ = case.measure(q_host, k, 40, 30, n, d, warm_s=0.3)
+        rec, res, _ = case.measure(q_host, k, 200, 30, n, d, warm_s=0.3)
         rec["planted_neighbours_found"] = bool((res[1].cpu().numpy()[qpos, 0] == planted).all())
         out[prec] = rec
         if prec == "bf16":  # the reference caller's loop: one retrieve() per query (main.py:270-271)
