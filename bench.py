@@ -505,7 +505,9 @@ def cfg_c1(ctx: Ctx, sample):
         case = SearchCase(ctx, index, 0, "cosine", b)
         # (30 warm-up calls: the GPU sat idle during the CPU baseline of the headline and a 0.4 ms step does not ramp
         #  the clocks by itself)
-        rec, res, _ = case.measure(q_host, k, 200, 30, n, d, warm_s=0.3)
+        # (100 timed steps: 3-5 launches per call, and a stream's backlog of ~1000 pending launches stalls the submitting
+        #  thread -- 200 steps of the fp32 path measured 1.24 ms per step against 0.45 with 40)
+        rec, res, _ = case.measure(q_host, k, 100, 30, n, d, warm_s=0.3)
         rec["planted_neighbours_found"] = bool((res[1].cpu().numpy()[qpos, 0] == planted).all())
         out[prec] = rec
         if prec == "bf16":  # the reference caller's loop: one retrieve() per query (main.py:270-271)
