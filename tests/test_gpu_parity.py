@@ -125,6 +125,11 @@ SHAPES = [
     (3000, 200, 768, 30),
     (40000, 1, 384, 10),
     (2500, 1500, 64, 10),
+    # a query tile that does not fit in shared memory (768-d: 5 K blocks resident, 7 streamed) with MANY query-tile
+    # pairs over a small corpus: every CTA pair changes segment (reloads the resident blocks, qfull / qempty parity)
+    # several times inside its range
+    (3000, 3000, 768, 10),
+    (1500, 2500, 640, 100),
     # k > 32: append-buffer selector (lists that never fill, fill once, compact many times)
     (3000, 40, 768, 100),
     (20000, 150, 384, 128),
@@ -225,7 +230,8 @@ FP32_TC_SHAPES = [
     (1, 1, 64, 1),
     (1000, 50, 32, 5),      # one K block per plane, K padding 32 -> 64
     (5000, 257, 100, 7),    # K padding 100 -> 128: two K blocks per plane, resident query planes
-    (20000, 300, 384, 10),  # six K blocks per plane: the query planes are streamed with the stages
+    (20000, 300, 384, 10),  # six K blocks per plane: five hi-plane blocks resident, the rest streamed with the stages
+    (3000, 3000, 384, 10),  # the same with many query-tile pairs per CTA pair: segment changes reload the resident blocks
     (3000, 40, 768, 100),
     (60000, 1500, 64, 100),
     (40000, 1, 384, 10),
