@@ -221,7 +221,8 @@ int lk_ae_set_precision(lk_ae* ae, int precision);
 /* x: m x d_in fp32 row-major; z: m x d_latent fp32 row-major.  Device buffers: asynchronous on `stream`.
  * Host buffers (either side): the rows go through in chunks of 32768 whose host-to-device copy, kernel and
  * device-to-host copy overlap (two staging buffers each way, the copies on streams of the handle); page-locked
- * host memory makes the copies run at link speed; the call returns when z is complete. */
+ * host memory makes the copies run at link speed (pageable rows are staged through page-locked blocks by a few
+ * threads of the library, as for lk_index_add and host queries); the call returns when z is complete. */
 int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int z_mem, void* stream);
 int lk_ae_destroy(lk_ae* ae);
 

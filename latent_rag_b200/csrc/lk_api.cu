@@ -70,6 +70,7 @@ struct lk_index {
   int* ticket = nullptr;  // completion counters of the single-launch small-batch search
   unsigned char* pin = nullptr;  // pinned, device-visible host staging of that path: queries | scores | ids
   size_t pin_cap = 0;
+  HostStager up;                 // host rows / queries -> device (pageable sources staged by threads)
   // fp32 storage on the tensor cores: split-bf16 planes of the rows (x = hi + lo), built lazily from the fp32
   // tiles by the first tcgen05 search and extended as rows are added; the fp32 tiles stay (exact FMA kernel)
   TileGeom gp;                    // geometry of the planes: kblocks = 2 * ceil(dim / 64)
@@ -99,6 +100,7 @@ struct lk_ae {
   // host inputs / outputs: two staging buffers each way, copies on their own streams so that the upload of chunk
   // i + 1 and the download of chunk i - 1 run under the kernel of chunk i
   Buf xin[2], zout[2];
+  HostStager up;
   cudaStream_t cs_in = nullptr, cs_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
@@ -131,6 +133,7 @@ int lk_index_destroy(lk_index* ix) {
   if (ix->err_flag) cudaFree(ix->err_flag);
   if (ix->ticket) cudaFree(ix->ticket);
   if (ix->pin) cudaFreeHost(ix->pin);
+  ix->up.release();
   if (ix->planes) cudaFree(ix->planes);
   Buf* bufs[] = {&ix->stage, &ix->white, &ix->q_tiles, &ix->q_side, &ix->q_planes, &ix->mtmp_s, &ix->mtmp_i, &ix->part_s, &ix->part_i, &ix->part_c,
                  &ix->out_s, &ix->out_i, &ix->debug, &ix->deep_s, &ix->deep_i, &ix->deep_last, &ix->deep_flags,
@@ -231,7 +234,7 @@ static int ingest_rows(lk_index* ix, const void* rows, int dtype, int mem, int64
     if (mem == LK_HOST) {
       int rc = ix->stage.ensure((size_t)kStageRows * ix->dim * in_elem);
       if (rc != LK_OK) return rc;
-      LK_CUDA(cudaMemcpyAsync(ix->stage.p, src, (size_t)cnt * ix->dim * in_elem, cudaMemcpyHostToDevice, st));
+      if ((rc = ix->up.upload(ix->stage.p, src, (size_t)cnt * ix->dim * in_elem, st)) != LK_OK) return rc;
       cur = ix->stage.p;
     }
     int cur_dtype = dtype;
@@ -933,6 +936,7 @@ int lk_ae_destroy(lk_ae* ae) {
     for (cudaEvent_t e : {ae->ev_in[i], ae->ev_comp[i], ae->ev_out[i]})
       if (e) cudaEventDestroy(e);
   }
+  ae->up.release();
   if (ae->cs_in) cudaStreamDestroy(ae->cs_in);
   if (ae->cs_out) cudaStreamDestroy(ae->cs_out);
   ae->xslabs.release();
@@ -1108,7 +1112,7 @@ int lk_ae_encode(lk_ae* ae, const float* x, int x_mem, int64_t m, float* z, int 
     float* zo = z + (size_t)done * ae->d_latent;
     if (host_in) {
       if (c >= 2) LK_CUDA(cudaStreamWaitEvent(ae->cs_in, ae->ev_comp[buf], 0));  // the kernel of chunk c - 2 read xin[buf]
-      LK_CUDA(cudaMemcpyAsync(ae->xin[buf].p, xin, (size_t)cnt * ae->d_in * 4, cudaMemcpyHostToDevice, ae->cs_in));
+      if ((rc = ae->up.upload(ae->xin[buf].p, xin, (size_t)cnt * ae->d_in * 4, ae->cs_in)) != LK_OK) return rc;
       LK_CUDA(cudaEventRecord(ae->ev_in[buf], ae->cs_in));
       LK_CUDA(cudaStreamWaitEvent(st, ae->ev_in[buf], 0));
       xin = ae->xin[buf].as<float>();
