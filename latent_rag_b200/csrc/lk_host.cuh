@@ -76,12 +76,18 @@ struct HostStager {
     }
     std::thread th[4];
     const size_t per = (n / t + 63) & ~(size_t)63;
-    for (unsigned i = 1; i < t; ++i) {
-      const size_t lo = i * per < n ? i * per : n, hi = (i + 1) * per < n ? (i + 1) * per : n;
-      th[i] = std::thread([=] { if (hi > lo) memcpy(dst + lo, src + lo, hi - lo); });
+    unsigned started = 1;
+    for (; started < t; ++started) {
+      const size_t lo = started * per < n ? started * per : n, hi = (started + 1) * per < n ? (started + 1) * per : n;
+      try {  // no exception may cross the C ABI: a thread that cannot start leaves its share to this one
+        th[started] = std::thread([=] { if (hi > lo) memcpy(dst + lo, src + lo, hi - lo); });
+      } catch (...) {
+        break;
+      }
     }
-    memcpy(dst, src, per < n ? per : n);
-    for (unsigned i = 1; i < t; ++i) th[i].join();
+    memcpy(dst, src, per < n ? per : n);  // share 0, and the shares [started, t) that no thread took
+    if (started < t && started * per < n) memcpy(dst + started * per, src + started * per, n - started * per);
+    for (unsigned i = 1; i < started; ++i) th[i].join();
   }
   int upload(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     if (bytes < (1u << 20) || !pageable(src)) {
