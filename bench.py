@@ -831,7 +831,8 @@ def main():
         line = {
             "metric": METRIC_NAME, "value": args.batch / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16 inputs, f32 accumulate", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16", "dtype_detail": "bf16 rows and queries, fp32 accumulate and scores",
+            "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {"value": args.batch / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(q_pin.numel() * 4), "d2h_bytes_per_step": int(args.batch * k * 12)},
