@@ -428,7 +428,16 @@ class SearchCase:
         q_pin = q_host.pin_memory()
         q_dev = q_host.to(ctx.dev)
         b = q_host.size(0)
-        ms_dev, _, out = ctx.timed(lambda q: self.step_device(q, k), q_dev, steps, warmup, warm_s)
+        step = lambda q: self.step_device(q, k)  # noqa: E731
+        if warm_s > 0 and ctx.world == 1 and steps >= 10:
+            # sub-millisecond steps are three to five launches each and a stall of the submitting thread shows up as idle
+            # GPU time (config 1 measured 0.36 .. 0.87 ms per step from run to run with an unchanged 0.314 ms kernel): the
+            # MEDIAN of five timed groups of steps / 5 ("median of >= 20"), not one group's mean
+            per = max(2, steps // 5)
+            first, _, out = ctx.timed(step, q_dev, per, warmup, warm_s)
+            ms_dev = statistics.median([first] + [ctx.timed(step, q_dev, per, 0)[0] for _ in range(4)])
+        else:
+            ms_dev, _, out = ctx.timed(step, q_dev, steps, warmup, warm_s)
         _, ms_e2e, out_e2e = ctx.timed(lambda q: self.step_e2e(q, k), q_pin, max(2, steps // 2), 1)
         kms, per_rank = ctx.kernel_ms(self.index, q_dev, k, self.lo, max(2, steps // 2))
         self.check()
